@@ -1,0 +1,284 @@
+// Fused multi-head self-attention backward on tcgen05/TMEM (backward of Attention.forward,
+// Dino/modules/vision_transformer.py:80-92; the reference gets it from autograd over the materialised
+// [2B,H,256,256] probabilities, here P is recomputed from the saved per-row log-sum-exp).
+//
+// One CTA per (sequence, head); Q,K,V,dO [256x64] bf16 resident in shared memory (TMA, SWIZZLE_128B), all five
+// contractions on tcgen05.mma with fp32 accumulators in TMEM (all 512 columns):
+//   for key tile j (128 keys), query tile i (128 queries):
+//     S^T  = K_j Q_i^T            [keys x queries]   cols [0,128)
+//     dP^T = V_j dO_i^T           [keys x queries]   cols [128,256)
+//     P^T  = exp2(S^T c - lse2[q]);  dS^T = P^T (dP^T - delta[q]) * scale     (thread = key row)
+//     dV_j += P^T  dO_i           cols [320,384)     (dO read MN-major)
+//     dK_j += dS^T Q_i            cols [256,320)     (Q  read MN-major)
+//     dQ_i += dS   K_j            cols [384,512)     (dS^T tile read MN-major as A, K read MN-major)
+// P^T / dS^T go through shared memory as bf16 in the 128B-swizzled layout that is simultaneously a K-major A tile
+// (for dV, dK) and an MN-major A tile (for dQ).
+#include "ccd_common.cuh"
+#include "tmap.cuh"
+
+namespace ccd {
+
+constexpr int ATB_N = 256;
+constexpr int ATB_D = 64;
+constexpr int ATB_THREADS = 192;
+
+struct MhsaBwdParams {
+  const bf16* o;      // [T, E] forward output
+  const bf16* d_o;    // [T, E]
+  const float* lse2;  // [S, H, 256]
+  bf16* dqkv;         // [T, 3E]
+  int E, H;
+  float scale, scale_log2;
+};
+
+struct MhsaBwdSmem {
+  static constexpr int TILE = ATB_N * ATB_D * 2;  // 32 KB
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = TILE;
+  static constexpr int OFF_V = 2 * TILE;
+  static constexpr int OFF_DO = 3 * TILE;
+  static constexpr int OFF_PT = 4 * TILE;   // [128 keys x 128 queries] bf16, two 64-query blocks of 16 KB
+  static constexpr int OFF_DST = 5 * TILE;
+  static constexpr int OFF_LSE = 6 * TILE;  // 256 f32
+  static constexpr int OFF_DELTA = OFF_LSE + 1024;
+  static constexpr int OFF_BAR = OFF_DELTA + 1024;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+};
+
+__device__ __forceinline__ float ex2_approx_b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
+  return bf16lo(a.x) * bf16lo(b.x) + bf16hi(a.x) * bf16hi(b.x) + bf16lo(a.y) * bf16lo(b.y) + bf16hi(a.y) * bf16hi(b.y) +
+         bf16lo(a.z) * bf16lo(b.z) + bf16hi(a.z) * bf16hi(b.z) + bf16lo(a.w) * bf16lo(b.w) + bf16hi(a.w) * bf16hi(b.w);
+}
+
+// 64 fp32 TMEM columns of this thread's lane -> bf16 -> 128 contiguous bytes in global memory
+__device__ __forceinline__ void store_tmem_row64(uint32_t taddr, bf16* dst) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t raw[32];
+    tmem_ld_32x32(taddr + half * 32, raw);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(raw[8 * g + 0]), __uint_as_float(raw[8 * g + 1]));
+      o.y = pack_bf16x2(__uint_as_float(raw[8 * g + 2]), __uint_as_float(raw[8 * g + 3]));
+      o.z = pack_bf16x2(__uint_as_float(raw[8 * g + 4]), __uint_as_float(raw[8 * g + 5]));
+      o.w = pack_bf16x2(__uint_as_float(raw[8 * g + 6]), __uint_as_float(raw[8 * g + 7]));
+      *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ATB_THREADS, 1)
+mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const MhsaBwdParams p) {
+  using L = MhsaBwdSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sPT = smem + L::OFF_PT;
+  uint8_t* sDST = smem + L::OFF_DST;
+  float* sLse = reinterpret_cast<float*>(smem + L::OFF_LSE);
+  float* sDelta = reinterpret_cast<float*>(smem + L::OFF_DELTA);
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* bar_vdo = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;    // S^T, dP^T ready in TMEM          (once per (j,i) pair)
+  uint64_t* bar_pd = bar_qk + 3;   // P^T, dS^T written to smem         (128 arrivals per pair)
+  uint64_t* bar_acc = bar_qk + 4;  // dV/dK/dQ MMAs of the pair retired (once per pair)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.x;
+  const int s = blockIdx.y;
+  const int row0 = s * ATB_N;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_vdo, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_pd, 128);
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tST = tmem_base, tDPT = tmem_base + 128, tDK = tmem_base + 256, tDV = tmem_base + 320,
+                 tDQ = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_qk, 2 * L::TILE);
+      for (int b = 0; b < 2; ++b) {
+        tma_load_2d(smem + L::OFF_Q + b * 16384, &tmQKV, bar_qk, h * ATB_D, row0 + b * 128);
+        tma_load_2d(smem + L::OFF_K + b * 16384, &tmQKV, bar_qk, p.E + h * ATB_D, row0 + b * 128);
+      }
+      mbar_arrive_expect_tx(bar_vdo, 2 * L::TILE);
+      for (int b = 0; b < 2; ++b) {
+        tma_load_2d(smem + L::OFF_V + b * 16384, &tmQKV, bar_vdo, 2 * p.E + h * ATB_D, row0 + b * 128);
+        tma_load_2d(smem + L::OFF_DO + b * 16384, &tmDO, bar_vdo, h * ATB_D, row0 + b * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t aQ = smem_u32(smem + L::OFF_Q), aK = smem_u32(smem + L::OFF_K), aV = smem_u32(smem + L::OFF_V),
+                     aDO = smem_u32(smem + L::OFF_DO), aPT = smem_u32(sPT), aDST = smem_u32(sDST);
+      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
+      const uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major
+      const uint32_t id_nn = umma_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major
+      mbar_wait(bar_qk, 0);
+      mbar_wait(bar_vdo, 0);
+      tc_fence_after();
+      for (int t = 0; t < 4; ++t) {
+        const int j = t >> 1, i = t & 1;
+        // S^T = K_j Q_i^T ; dP^T = V_j dO_i^T      (K = 64 -> 4 k-steps of 32 B inside the swizzle row)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tST, umma_smem_desc_sw128(aK + j * 16384 + ks * 32, 16, 1024),
+                  umma_smem_desc_sw128(aQ + i * 16384 + ks * 32, 16, 1024), id_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tDPT, umma_smem_desc_sw128(aV + j * 16384 + ks * 32, 16, 1024),
+                  umma_smem_desc_sw128(aDO + i * 16384 + ks * 32, 16, 1024), id_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        mbar_wait(bar_pd, t & 1);
+        tc_fence_after();
+        // contractions over the 128 queries / keys of the pair: 8 k-steps
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t a_k = (uint32_t)((ks >> 2) * 16384 + (ks & 3) * 32);  // K-major A inside P^T / dS^T
+          // dV_j += P^T dO_i
+          umma_ss(tDV, umma_smem_desc_sw128(aPT + a_k, 16, 1024),
+                  umma_smem_desc_sw128(aDO + i * 16384 + ks * 2048, 8192, 1024), id_kn, (i > 0 || ks > 0) ? 1u : 0u);
+          // dK_j += dS^T Q_i
+          umma_ss(tDK, umma_smem_desc_sw128(aDST + a_k, 16, 1024),
+                  umma_smem_desc_sw128(aQ + i * 16384 + ks * 2048, 8192, 1024), id_kn, (i > 0 || ks > 0) ? 1u : 0u);
+          // dQ_i += dS K_j      (A = dS^T tile read MN-major: 64-query chunks 16 KB apart, 16 key-rows = 2048 B)
+          umma_ss(tDQ + i * 64, umma_smem_desc_sw128(aDST + ks * 2048, 16384, 1024),
+                  umma_smem_desc_sw128(aK + j * 16384 + ks * 2048, 8192, 1024), id_nn, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;  // key row within tile j / query row in the epilogues
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    // delta[q] = sum_d O[q,d] dO[q,d]; lse2 -> smem
+    for (int rr = r; rr < ATB_N; rr += 128) {
+      const bf16* po = p.o + ((size_t)row0 + rr) * p.E + h * ATB_D;
+      const bf16* pd = p.d_o + ((size_t)row0 + rr) * p.E + h * ATB_D;
+      float acc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        acc += dot8_bf16(*reinterpret_cast<const uint4*>(po + g * 8), *reinterpret_cast<const uint4*>(pd + g * 8));
+      sDelta[rr] = acc;
+      sLse[rr] = p.lse2[((size_t)s * p.H + h) * ATB_N + rr];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const float c = p.scale_log2;
+
+    for (int t = 0; t < 4; ++t) {
+      const int j = t >> 1, i = t & 1;
+      mbar_wait(bar_s, t & 1);
+      if (t > 0) mbar_wait(bar_acc, (t - 1) & 1);   // previous pair's MMAs no longer read P^T / dS^T smem
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {  // 32 queries per chunk
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32(tST + lane_sel + ch * 32, rs);
+        tmem_ld_32x32(tDPT + lane_sel + ch * 32, rd);
+        tmem_wait_ld();
+        uint32_t pp[16], dd[16];
+        const float* lse = sLse + i * 128 + ch * 32;
+        const float* del = sDelta + i * 128 + ch * 32;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = ex2_approx_b(fmaf(__uint_as_float(rs[2 * e]), c, -lse[2 * e]));
+          const float p1 = ex2_approx_b(fmaf(__uint_as_float(rs[2 * e + 1]), c, -lse[2 * e + 1]));
+          const float d0 = p0 * (__uint_as_float(rd[2 * e]) - del[2 * e]) * p.scale;
+          const float d1 = p1 * (__uint_as_float(rd[2 * e + 1]) - del[2 * e + 1]) * p.scale;
+          pp[e] = pack_bf16x2(p0, p1);
+          dd[e] = pack_bf16x2(d0, d1);
+        }
+        const int boff = (ch >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const int chunk = (((ch & 1) * 4 + v4) ^ (r & 7)) * 16;
+          *reinterpret_cast<uint4*>(sPT + boff + chunk) = make_uint4(pp[4 * v4], pp[4 * v4 + 1], pp[4 * v4 + 2], pp[4 * v4 + 3]);
+          *reinterpret_cast<uint4*>(sDST + boff + chunk) = make_uint4(dd[4 * v4], dd[4 * v4 + 1], dd[4 * v4 + 2], dd[4 * v4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pd);
+      if (i == 1) {
+        // key tile j finished: dK_j, dV_j -> dqkv
+        mbar_wait(bar_acc, t & 1);
+        tc_fence_after();
+        bf16* drow = p.dqkv + ((size_t)row0 + j * 128 + r) * (3 * p.E) + h * ATB_D;
+        store_tmem_row64(tDK + lane_sel, drow + p.E);
+        store_tmem_row64(tDV + lane_sel, drow + 2 * p.E);
+        tc_fence_before();
+      }
+    }
+    // dQ tiles (bar_acc of the last pair has been waited on above)
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      bf16* drow = p.dqkv + ((size_t)row0 + i * 128 + r) * (3 * p.E) + h * ATB_D;
+      store_tmem_row64(tDQ + i * 64 + lane_sel, drow);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace ccd
+
+using namespace ccd;
+
+// C ABI -- see include/ccd_b200.h
+extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int S,
+                            int H, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!qkv || !o || !d_o || !lse2 || !dqkv || S <= 0 || H <= 0) return CCD_ERR_ARG;
+  const int E = H * ATB_D;
+  CUtensorMap tmQKV, tmDO;
+  if (!get_tmap_bf16_2d(&tmQKV, qkv, (uint64_t)S * ATB_N, (uint64_t)3 * E, (uint64_t)3 * E, 128, 64)) return CCD_ERR_TMAP;
+  if (!get_tmap_bf16_2d(&tmDO, d_o, (uint64_t)S * ATB_N, (uint64_t)E, (uint64_t)E, 128, 64)) return CCD_ERR_TMAP;
+  MhsaBwdParams p;
+  p.o = reinterpret_cast<const bf16*>(o);
+  p.d_o = reinterpret_cast<const bf16*>(d_o);
+  p.lse2 = lse2;
+  p.dqkv = reinterpret_cast<bf16*>(dqkv);
+  p.E = E;
+  p.H = H;
+  p.scale = 0.125f;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(mhsa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        MhsaBwdSmem::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(H, S);
+  mhsa_bwd_kernel<<<grid, ATB_THREADS, MhsaBwdSmem::SMEM_BYTES, stream>>>(tmQKV, tmDO, p);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}

@@ -1,0 +1,251 @@
+// Fused multi-head self-attention forward on tcgen05/TMEM for the CCD ViT encoder
+// (reference: Attention.forward, Dino/modules/vision_transformer.py:80-92 -- softmax(q k^T * hd^-0.5) v over
+//  N = 256 tokens, head_dim 64, no mask, no dropout).  The reference materialises [2B,H,256,256] fp32 scores;
+//  here scores never leave the SM.
+//
+// One CTA per (sequence, head, 128-query tile); two CTAs co-resident per SM (80 KB smem, 256 TMEM columns each) so
+// one CTA's softmax overlaps the other's MMAs.
+//   warp 0   : TMA producer -- Q tile [128x64], K [256x64], V [256x64] straight out of the fused qkv activation
+//              [T, 3E] (no head-split copies), SWIZZLE_128B
+//   warp 1   : TMEM alloc + UMMA issuer:  S[128x256] = Q K^T  (4 x tcgen05.mma 128x256x16, fp32 in TMEM cols 0..255)
+//                                         O[128x64]  = P V    (16 x tcgen05.mma 128x64x16; V read MN-major)
+//   warps 2-5: one query row per thread: row max, exp2 with folded scale, bf16 P written back over S
+//              (TMEM cols 0..127, A-operand of the second MMA; P_IN_TMEM) or into smem (fallback layout),
+//              then O / rowsum -> bf16 out[T,E], and the per-row log2-sum-exp for backward.
+#include "ccd_common.cuh"
+#include "tmap.cuh"
+
+namespace ccd {
+
+constexpr int ATT_N = 256;    // tokens per sequence (8x32 grid, no CLS: vision_transformer.py:229-238)
+constexpr int ATT_D = 64;     // head dim (all three archs)
+constexpr int ATT_BM = 128;   // query rows per CTA
+constexpr int ATT_THREADS = 192;
+
+struct MhsaFwdParams {
+  bf16* out;        // [T, E]
+  float* lse2;      // [S, H, 256]  log2-domain: max*c + log2(sum),  c = scale*log2(e)
+  int E, H;
+  float scale_log2;  // hd^-0.5 * log2(e)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool P_IN_TMEM>
+struct MhsaFwdCfg {
+  static constexpr int Q_BYTES = ATT_BM * ATT_D * 2;   // 16 KB
+  static constexpr int KV_BYTES = ATT_N * ATT_D * 2;   // 32 KB
+  static constexpr int P_BYTES = P_IN_TMEM ? 0 : ATT_BM * ATT_N * 2;  // 64 KB
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+};
+
+template <bool P_IN_TMEM>
+__global__ void __launch_bounds__(ATT_THREADS, P_IN_TMEM ? 2 : 1)
+mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const MhsaFwdParams p) {
+  using Cfg = MhsaFwdCfg<P_IN_TMEM>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sP = smem + Cfg::OFF_P;
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;
+  uint64_t* bar_p = bar_qk + 3;
+  uint64_t* bar_o = bar_qk + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;   // query tile 0/1
+  const int h = blockIdx.y;
+  const int s = blockIdx.z;
+  const int row0 = s * ATT_N;  // first token row of this sequence in [T, 3E]
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQKV);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;          // S: cols [0,256)
+  const uint32_t tP = tmem_base;          // P (bf16 pairs) aliases cols [0,128)
+  const uint32_t tO = tmem_base + 128;    // O: cols [128,192) -- free once S has been consumed
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_qk, Cfg::Q_BYTES + Cfg::KV_BYTES);
+      tma_load_2d(sQ, &tmQKV, bar_qk, h * ATT_D, row0 + mt * ATT_BM);
+      tma_load_2d(sK, &tmQKV, bar_qk, p.E + h * ATT_D, row0);
+      tma_load_2d(sK + 16384, &tmQKV, bar_qk, p.E + h * ATT_D, row0 + 128);
+      mbar_arrive_expect_tx(bar_v, Cfg::KV_BYTES);
+      tma_load_2d(sV, &tmQKV, bar_v, 2 * p.E + h * ATT_D, row0);
+      tma_load_2d(sV + 16384, &tmQKV, bar_v, 2 * p.E + h * ATT_D, row0 + 128);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- S = Q K^T : M=128, N=256, K=64 (4 k-steps), both operands K-major ----
+      const uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k)
+        umma_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024), umma_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+      // ---- O = P V : M=128, N=64, K=256 (16 k-steps); V[token, hd] is the MN-major B operand ----
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+#pragma unroll
+      for (int k = 0; k < ATT_N / 16; ++k) {
+        const uint64_t dv = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
+        if constexpr (P_IN_TMEM) {
+          umma_ts(tO, tP + k * 8, dv, idesc_o, k > 0 ? 1u : 0u);  // 16 bf16 = 8 TMEM columns per k-step
+        } else {
+          const uint64_t dp = umma_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          umma_ss(tO, dp, dv, idesc_o, k > 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ---- softmax + epilogue: thread <-> query row (TMEM lane) ----
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                         // row within the tile
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const float c = p.scale_log2;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < ATT_N / 32; ++ch) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tS + lane_sel + ch * 32, raw);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+    }
+    const float mc = mx * c;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < ATT_N / 32; ++ch) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tS + lane_sel + ch * 32, raw);
+      tmem_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * j]), c, -mc));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * j + 1]), c, -mc));
+        pk[j] = pack_bf16x2(p0, p1);
+        sum += bf16lo(pk[j]) + bf16hi(pk[j]);   // sum the rounded values: P V / sum(P) stays a convex combination
+      }
+      if constexpr (P_IN_TMEM) {
+        tmem_st_32x16(tP + lane_sel + ch * 16, pk);
+      } else {
+        // K-major SWIZZLE_128B tile: 64-key block kb at kb*16 KB, row r at r*128 B, 16-byte chunk index ^ (r & 7)
+        uint8_t* rowp = sP + (ch >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const int chunk = ((ch & 1) * 4 + v4) ^ (r & 7);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[4 * v4], pk[4 * v4 + 1], pk[4 * v4 + 2], pk[4 * v4 + 3]);
+        }
+      }
+    }
+    if constexpr (P_IN_TMEM) {
+      tmem_wait_st();
+      tc_fence_before();
+    } else {
+      fence_proxy_async_smem();
+    }
+    mbar_arrive(bar_p);
+
+    // ---- epilogue ----
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    const size_t tok = (size_t)row0 + mt * ATT_BM + r;
+    bf16* orow = p.out + tok * p.E + h * ATT_D;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tO + lane_sel + half * 32, raw);
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(raw[8 * g + 0]) * inv, __uint_as_float(raw[8 * g + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(raw[8 * g + 2]) * inv, __uint_as_float(raw[8 * g + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(raw[8 * g + 4]) * inv, __uint_as_float(raw[8 * g + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(raw[8 * g + 6]) * inv, __uint_as_float(raw[8 * g + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + half * 32 + g * 8) = o;
+      }
+    }
+    if (p.lse2 != nullptr) p.lse2[((size_t)s * p.H + h) * ATT_N + mt * ATT_BM + r] = mc + log2f(sum);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+template <bool P_IN_TMEM>
+static int launch_mhsa_fwd(const CUtensorMap& tm, const MhsaFwdParams& p, int S, cudaStream_t stream) {
+  using Cfg = MhsaFwdCfg<P_IN_TMEM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(mhsa_fwd_kernel<P_IN_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(ATT_N / ATT_BM, p.H, S);
+  mhsa_fwd_kernel<P_IN_TMEM><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, p);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+}  // namespace ccd
+
+using namespace ccd;
+
+// C ABI -- see include/ccd_b200.h
+extern "C" int ccd_mhsa_fwd(const void* qkv, void* out, float* lse2, int S, int H, int variant, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!qkv || !out || S <= 0 || H <= 0) return CCD_ERR_ARG;
+  const int E = H * ATT_D;
+  CUtensorMap tm;
+  if (!get_tmap_bf16_2d(&tm, qkv, (uint64_t)S * ATT_N, (uint64_t)3 * E, (uint64_t)3 * E, 128, 64)) return CCD_ERR_TMAP;
+  MhsaFwdParams p;
+  p.out = reinterpret_cast<bf16*>(out);
+  p.lse2 = lse2;
+  p.E = E;
+  p.H = H;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  if (variant == 1) return launch_mhsa_fwd<false>(tm, p, S, stream);
+  return launch_mhsa_fwd<true>(tm, p, S, stream);
+}

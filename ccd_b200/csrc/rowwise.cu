@@ -1,0 +1,437 @@
+// Row-wise HBM-bound kernels of the CCD encoder / DINO head: LayerNorm fwd/bwd (eps 1e-6,
+// Dino/modules/vision_transformer.py:108-110,247,250), bias-gradient column sums, L2 row normalisation and the
+// weight-norm reparametrisation of DINOHead.last_layer (vision_transformer.py:313-316,326), multi-tensor cast / EMA
+// (train.py:264-272).  One warp per row, float4 / 16-byte accesses, warp-shuffle reductions.
+#include "ccd_common.cuh"
+
+namespace ccd {
+
+constexpr int LN_MAX_V4 = 4;  // E <= 512 -> at most 4 float4 per lane
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm forward: x f32 [rows,E] -> y (bf16 and/or f32)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ y_bf16,
+                                                            float* __restrict__ y_f32, int rows, int E, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nv = E >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * E);
+  float4 v[LN_MAX_V4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      v[i] = xr[c];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / (float)E;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (y_f32) reinterpret_cast<float4*>(y_f32 + (size_t)warp * E)[c] = o;
+      if (y_bf16) {
+        uint2 pk = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        reinterpret_cast<uint2*>(y_bf16 + (size_t)warp * E)[c] = pk;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm backward (recomputes mean/rstd from x): dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) + resid,
+// g = dy*gamma.  dgamma/dbeta accumulated per CTA then atomically into [E] (pre-zeroed by the caller).
+// ---------------------------------------------------------------------------------------------------------
+template <bool DY_BF16>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const void* __restrict__ dy_, const float* __restrict__ resid,
+                                                            float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int rows, int E, float eps) {
+  __shared__ float s_dg[512], s_db[512];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int nv = E >> 2;
+  float4 adg[LN_MAX_V4], adb[LN_MAX_V4];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) { adg[i] = make_float4(0, 0, 0, 0); adb[i] = make_float4(0, 0, 0, 0); }
+
+  for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * E);
+    float4 v[LN_MAX_V4], g[LN_MAX_V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) { v[i] = xr[c]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+    }
+    const float mean = warp_sum(s) / (float)E;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 d;
+        if constexpr (DY_BF16) {
+          const uint2 pk = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (size_t)row * E)[c];
+          d = make_float4(bf16lo(pk.x), bf16hi(pk.x), bf16lo(pk.y), bf16hi(pk.y));
+        } else {
+          d = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * E)[c];
+        }
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
+        adg[i].x += d.x * v[i].x; adg[i].y += d.y * v[i].y; adg[i].z += d.z * v[i].z; adg[i].w += d.w * v[i].w;
+        adb[i].x += d.x; adb[i].y += d.y; adb[i].z += d.z; adb[i].w += d.w;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        m1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        m2 += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+      }
+    }
+    m1 = warp_sum(m1) / (float)E;
+    m2 = warp_sum(m2) / (float)E;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 o;
+        o.x = rstd * (g[i].x - m1 - v[i].x * m2);
+        o.y = rstd * (g[i].y - m1 - v[i].y * m2);
+        o.z = rstd * (g[i].z - m1 - v[i].z * m2);
+        o.w = rstd * (g[i].w - m1 - v[i].w * m2);
+        if (resid) {
+          const float4 r = reinterpret_cast<const float4*>(resid + (size_t)row * E)[c];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (dx_f32) reinterpret_cast<float4*>(dx_f32 + (size_t)row * E)[c] = o;
+        if (dx_bf16)
+          reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * E)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      atomicAdd(&s_dg[4 * c + 0], adg[i].x); atomicAdd(&s_dg[4 * c + 1], adg[i].y);
+      atomicAdd(&s_dg[4 * c + 2], adg[i].z); atomicAdd(&s_dg[4 * c + 3], adg[i].w);
+      atomicAdd(&s_db[4 * c + 0], adb[i].x); atomicAdd(&s_db[4 * c + 1], adb[i].y);
+      atomicAdd(&s_db[4 * c + 2], adb[i].z); atomicAdd(&s_db[4 * c + 3], adb[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    atomicAdd(dgamma + i, s_dg[i]);
+    atomicAdd(dbeta + i, s_db[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out[c] += sum_r x[r,c]   (bias gradients), x bf16 [rows, cols], cols % 8 == 0, out pre-zeroed
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS_PER_BLOCK = 256;
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows,
+                                                          int cols) {
+  __shared__ float red[8][32][8];
+  const int cg = blockIdx.x * 32 + threadIdx.x;  // column group of 8
+  const int r0 = blockIdx.y * CS_ROWS_PER_BLOCK;
+  const int r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cg * 8 < cols) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + (size_t)r * cols + cg * 8);
+      a[0] += bf16lo(v.x); a[1] += bf16hi(v.x); a[2] += bf16lo(v.y); a[3] += bf16hi(v.y);
+      a[4] += bf16lo(v.z); a[5] += bf16hi(v.z); a[6] += bf16lo(v.w); a[7] += bf16hi(v.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = a[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && cg * 8 < cols) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][j];
+      atomicAdd(out + cg * 8 + j, t);
+    }
+  }
+}
+
+// out[c] = sum_r x[r,c]   f32 [rows, cols] (teacher-centre batch sum, Dino/loss/Dino_loss.py:138); out pre-zeroed
+__global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int rows,
+                                                         int cols, int rows_per_block) {
+  const int c4 = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column
+  if (c4 * 4 >= cols) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float4 a = make_float4(0, 0, 0, 0);
+  for (int r = r0; r < r1; ++r) {
+    const float4 v = reinterpret_cast<const float4*>(x + (size_t)r * cols)[c4];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  atomicAdd(out + 4 * c4 + 0, a.x); atomicAdd(out + 4 * c4 + 1, a.y);
+  atomicAdd(out + 4 * c4 + 2, a.z); atomicAdd(out + 4 * c4 + 3, a.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// L2 row normalisation (F.normalize, eps 1e-12) fwd/bwd over [rows, 256]; weight-norm of last_layer
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ y,
+                                                         float* __restrict__ inv_norm, int rows, int cols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float v = x[(size_t)row * cols + c]; s += v * v; }
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+  for (int c = lane; c < cols; c += 32) y[(size_t)row * cols + c] = __float2bfloat16(x[(size_t)row * cols + c] * inv);
+  if (lane == 0) inv_norm[row] = inv;
+}
+// dx = inv * (dy - yhat * (yhat . dy)), yhat = x*inv (recomputed in fp32)
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ inv_norm,
+                                                         const float* __restrict__ dy, bf16* __restrict__ dx, int rows,
+                                                         int cols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float inv = inv_norm[row];
+  float dot = 0.f;
+  for (int c = lane; c < cols; c += 32) dot += x[(size_t)row * cols + c] * inv * dy[(size_t)row * cols + c];
+  dot = warp_sum(dot);
+  for (int c = lane; c < cols; c += 32) {
+    const float yh = x[(size_t)row * cols + c] * inv;
+    dx[(size_t)row * cols + c] = __float2bfloat16(inv * (dy[(size_t)row * cols + c] - yh * dot));
+  }
+}
+// w = v * g / ||v||  (row-wise over [K, cols]); writes bf16 w and inv_norm
+__global__ void __launch_bounds__(256) weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                             bf16* __restrict__ w, float* __restrict__ inv_norm, int rows,
+                                                             int cols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float t = v[(size_t)row * cols + c]; s += t * t; }
+  const float inv = rsqrtf(warp_sum(s));
+  const float sc = g[row] * inv;
+  for (int c = lane; c < cols; c += 32) w[(size_t)row * cols + c] = __float2bfloat16(v[(size_t)row * cols + c] * sc);
+  if (lane == 0) inv_norm[row] = inv;
+}
+// dg = (dW . v) * inv ;  dv = g*inv * (dW - vhat * (dW . vhat)),  vhat = v*inv
+__global__ void __launch_bounds__(256) weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                             const float* __restrict__ g, const float* __restrict__ inv_norm,
+                                                             float* __restrict__ dv, float* __restrict__ dg, int rows, int cols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float inv = inv_norm[row];
+  float dot = 0.f;
+  for (int c = lane; c < cols; c += 32) dot += dw[(size_t)row * cols + c] * v[(size_t)row * cols + c];
+  dot = warp_sum(dot) * inv;  // dW . vhat
+  const float sc = g[row] * inv;
+  for (int c = lane; c < cols; c += 32)
+    dv[(size_t)row * cols + c] = sc * (dw[(size_t)row * cols + c] - v[(size_t)row * cols + c] * inv * dot);
+  if (lane == 0 && dg) dg[row] = dot;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// multi-tensor kernels over a chunk table: int64 [n_chunks, 3] = (src_ptr, dst_ptr, n_elems <= 65536*?)
+// ---------------------------------------------------------------------------------------------------------
+enum MultiOp { MT_CAST_BF16 = 0, MT_EMA = 1, MT_SCALE = 2 };
+template <int OP>
+__global__ void __launch_bounds__(256) multi_tensor_kernel(const long long* __restrict__ table, float a, float b) {
+  const long long* e = table + (size_t)blockIdx.x * 3;
+  const float* src = reinterpret_cast<const float*>(e[0]);
+  const int n = (int)e[2];
+  if constexpr (OP == MT_CAST_BF16) {
+    bf16* dst = reinterpret_cast<bf16*>(e[1]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16(src[i]);
+  } else if constexpr (OP == MT_EMA) {   // dst = a*dst + b*src   (teacher EMA, train.py:268-272)
+    float* dst = reinterpret_cast<float*>(e[1]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = a * dst[i] + b * src[i];
+  } else {                               // dst = a*src
+    float* dst = reinterpret_cast<float*>(e[1]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = a * src[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else {
+    for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+
+// centre EMA with the reference's divisor quirk: c = c*m + (sum / denom)*(1-m)   (Dino_loss.py:140-143)
+__global__ void center_ema_kernel(float* __restrict__ center, const float* __restrict__ sum, float inv_denom, float m, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) center[i] = center[i] * m + sum[i] * inv_denom * (1.0f - m);
+}
+
+// im2col for the 4x4/stride-4 patch embedding (vision_transformer.py:126-131): x f32 [N,3,32,128] ->
+// cols bf16 [N*256, 64] with k = c*16 + ky*4 + kx (conv weight [E,3,4,4] flattened), k in [48,64) zero padded.
+__global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ cols, int n_img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (token, c, ky) -> 4 contiguous kx
+  const int total = n_img * 256 * 16;
+  if (idx >= total) return;
+  const int part = idx & 15;           // 0..11 real (c*4+ky), 12..15 padding
+  const int tok = idx >> 4;
+  bf16* dst = cols + (size_t)tok * 64 + part * 4;
+  if (part >= 12) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(0u, 0u);
+    return;
+  }
+  const int img = tok >> 8, t = tok & 255, py = t >> 5, px = t & 31;
+  const int c = part >> 2, ky = part & 3;
+  const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)img * 3 + c) * 32 + (py * 4 + ky)) * 128 + px * 4);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+}  // namespace ccd
+
+using namespace ccd;
+
+extern "C" int ccd_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                                 int rows, int E, float eps, void* stream) {
+  if (!x || !gamma || !beta || rows <= 0 || E <= 0 || (E & 3) || E > 512) return CCD_ERR_ARG;
+  const int blocks = (rows + 7) / 8;
+  layernorm_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, (bf16*)y_bf16, y_f32, rows, E, eps);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_is_bf16, const float* resid,
+                                 float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int rows, int E, float eps,
+                                 void* stream) {
+  if (!x || !gamma || !dy || !dgamma || !dbeta || rows <= 0 || (E & 3) || E > 512) return CCD_ERR_ARG;
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dy_is_bf16)
+    layernorm_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma,
+                                                                          dbeta, rows, E, eps);
+  else
+    layernorm_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma,
+                                                                           dbeta, rows, E, eps);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_colsum_bf16(const void* x, float* out, int rows, int cols, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0 || (cols & 7)) return CCD_ERR_ARG;
+  dim3 grid((cols + 255) / 256, (rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK);
+  colsum_bf16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, cols);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_colsum_f32(const float* x, float* out, int rows, int cols, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0 || (cols & 3)) return CCD_ERR_ARG;
+  const int rpb = 64;
+  dim3 grid((cols / 4 + 255) / 256, (rows + rpb - 1) / rpb);
+  colsum_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, rows, cols, rpb);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_l2norm_fwd(const float* x, void* y_bf16, float* inv_norm, int rows, int cols, void* stream) {
+  if (!x || !y_bf16 || !inv_norm || rows <= 0) return CCD_ERR_ARG;
+  l2norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y_bf16, inv_norm, rows, cols);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+extern "C" int ccd_l2norm_bwd(const float* x, const float* inv_norm, const float* dy, void* dx_bf16, int rows, int cols,
+                              void* stream) {
+  if (!x || !dy || !dx_bf16 || !inv_norm || rows <= 0) return CCD_ERR_ARG;
+  l2norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, inv_norm, dy, (bf16*)dx_bf16, rows, cols);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+extern "C" int ccd_weightnorm_fwd(const float* v, const float* g, void* w_bf16, float* inv_norm, int rows, int cols,
+                                  void* stream) {
+  if (!v || !g || !w_bf16 || !inv_norm || rows <= 0) return CCD_ERR_ARG;
+  weightnorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(v, g, (bf16*)w_bf16, inv_norm, rows, cols);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+extern "C" int ccd_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv,
+                                  float* dg, int rows, int cols, void* stream) {
+  if (!dw || !v || !g || !inv_norm || !dv || rows <= 0) return CCD_ERR_ARG;
+  weightnorm_bwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dw, v, g, inv_norm, dv, dg, rows, cols);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_multi_tensor(int op, const void* table_dev, int n_chunks, float a, float b, void* stream) {
+  if (!table_dev || n_chunks <= 0) return CCD_ERR_ARG;
+  const long long* t = (const long long*)table_dev;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (op) {
+    case MT_CAST_BF16: multi_tensor_kernel<MT_CAST_BF16><<<n_chunks, 256, 0, s>>>(t, a, b); break;
+    case MT_EMA: multi_tensor_kernel<MT_EMA><<<n_chunks, 256, 0, s>>>(t, a, b); break;
+    case MT_SCALE: multi_tensor_kernel<MT_SCALE><<<n_chunks, 256, 0, s>>>(t, a, b); break;
+    default: return CCD_ERR_ARG;
+  }
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (!src || !dst || n <= 0) return CCD_ERR_ARG;
+  const long long threads = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, (size_t)n);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_center_ema(float* center, const float* sum, float denom, float momentum, int n, void* stream) {
+  if (!center || !sum || n <= 0 || denom <= 0.f) return CCD_ERR_ARG;
+  center_ema_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(center, sum, 1.0f / denom, momentum, n);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_patch_im2col(const float* x, void* cols_bf16, int n_img, void* stream) {
+  if (!x || !cols_bf16 || n_img <= 0) return CCD_ERR_ARG;
+  const int total = n_img * 256 * 16;
+  patch_im2col_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)cols_bf16, n_img);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}

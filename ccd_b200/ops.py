@@ -1,0 +1,325 @@
+"""Thin torch-tensor wrappers over the C ABI (include/ccd_b200.h).  PyTorch is plumbing only here: device memory,
+the current CUDA stream and autograd bookkeeping; every computation below is a hand-written sm_100a kernel.
+No CPU / eager fallback exists -- a missing library or a non-CUDA tensor raises.
+"""
+import ctypes
+import re
+
+import torch
+
+from . import lib as _lib
+
+EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32, EPI_DGELU, EPI_POS = 0, 1, 2, 3, 4, 5
+MT_CAST_BF16, MT_EMA, MT_SCALE = 0, 1, 2
+LN_EPS = 1e-6
+SLOTS = 26
+
+_CTYPE = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong}
+_FN = {}
+LAUNCHES = [0]     # number of kernel-launching C-ABI calls (bench.py reports it)
+
+
+def _bind():
+    if _FN:
+        return
+    L = _lib.load()
+    with open(_lib.HEADER) as f:
+        text = f.read()
+    for m in re.finditer(r"^int\s+(ccd_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.M | re.S):
+        name, args = m.group(1), m.group(2)
+        fn = getattr(L, name)
+        types = []
+        if args.strip() not in ("", "void"):
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    types.append(ctypes.c_void_p)
+                else:
+                    types.append(_CTYPE[" ".join(a.split()[:-1]).replace("const ", "").strip()])
+        fn.argtypes = types
+        fn.restype = ctypes.c_int
+        _FN[name] = fn
+
+
+def _call(name, *args):
+    _bind()
+    rc = _FN[name](*args)
+    LAUNCHES[0] += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed with code {rc}")
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("ccd_b200 ops need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype):
+    assert t.dtype == dtype and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------------
+def gemm(A, B, M, N, K, a_mn=0, b_mn=0, epi=EPI_BF16, bias=None, out0=None, out1=None, aux=None, ldc=0, splits=1):
+    """C[M,N] = A[M,K] B[N,K]^T on tcgen05.  See include/ccd_b200.h:ccd_gemm_bf16."""
+    _call("ccd_gemm_bf16", _p(A), _p(B), M, N, K, a_mn, b_mn, epi, _p(bias), _p(out0), _p(out1), _p(aux), ldc, splits, _s())
+    return out0
+
+
+def wgrad_splits(n_out, k_in, t_rows):
+    tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+    kb = (t_rows + 63) // 64
+    return max(1, min(kb, (296 + tiles - 1) // tiles))
+
+
+def linear_fwd(x_bf16, w_bf16, bias, epi, out0, out1=None, aux=None):
+    """x [T,K] bf16, w [N,K] bf16 (nn.Linear layout)."""
+    T, K = x_bf16.shape
+    N = w_bf16.shape[0]
+    return gemm(x_bf16, w_bf16, T, N, K, 0, 0, epi, bias, out0, out1, aux)
+
+
+def linear_dgrad(dy_bf16, w_bf16, epi, out0, aux=None):
+    """dx [T,K] = dy [T,N] @ w [N,K]: w is read MN-major (no transpose copy)."""
+    T, N = dy_bf16.shape
+    K = w_bf16.shape[1]
+    return gemm(dy_bf16, w_bf16, T, K, N, 0, 1, epi, None, out0, None, aux)
+
+
+def linear_wgrad(dy_bf16, x_bf16, dw_f32_zeroed):
+    """dw [N,K] += dy[T,N]^T @ x[T,K]: both activations read MN-major; split-K over T with fp32 atomics."""
+    T, N = dy_bf16.shape
+    K = x_bf16.shape[1]
+    sp = wgrad_splits(N, K, T)
+    return gemm(dy_bf16, x_bf16, N, K, T, 1, 1, EPI_F32, None, dw_f32_zeroed, None, None, dw_f32_zeroed.shape[1], sp)
+
+
+def mhsa_fwd(qkv, S, H, want_lse=True, variant=0):
+    E = H * 64
+    out = torch.empty(S * 256, E, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(S, H, 256, dtype=torch.float32, device=qkv.device) if want_lse else None
+    _call("ccd_mhsa_fwd", _p(_chk(qkv, torch.bfloat16)), _p(out), _p(lse), S, H, variant, _s())
+    return out, lse
+
+
+def mhsa_bwd(qkv, o, d_o, lse, S, H):
+    dqkv = torch.empty_like(qkv)
+    _call("ccd_mhsa_bwd", _p(qkv), _p(o), _p(_chk(d_o, torch.bfloat16)), _p(lse), _p(dqkv), S, H, _s())
+    return dqkv
+
+
+def layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=False):
+    rows, E = x.shape
+    yb = torch.empty(rows, E, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    yf = torch.empty(rows, E, dtype=torch.float32, device=x.device) if want_f32 else None
+    _call("ccd_layernorm_fwd", _p(_chk(x, torch.float32)), _p(gamma), _p(beta), _p(yb), _p(yf), rows, E, LN_EPS, _s())
+    return yb, yf
+
+
+def layernorm_bwd(x, gamma, dy, resid, dgamma, dbeta, want_f32=True, want_bf16=True):
+    rows, E = x.shape
+    assert dy.is_contiguous() and dy.shape == x.shape
+    dxf = torch.empty(rows, E, dtype=torch.float32, device=x.device) if want_f32 else None
+    dxb = torch.empty(rows, E, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    _call("ccd_layernorm_bwd", _p(x), _p(gamma), _p(dy), 1 if dy.dtype == torch.bfloat16 else 0, _p(resid), _p(dxf), _p(dxb),
+          _p(dgamma), _p(dbeta), rows, E, LN_EPS, _s())
+    return dxf, dxb
+
+
+def colsum_bf16(x, out_zeroed):
+    _call("ccd_colsum_bf16", _p(_chk(x, torch.bfloat16)), _p(out_zeroed), x.shape[0], x.shape[1], _s())
+    return out_zeroed
+
+
+def colsum_f32(x, out_zeroed):
+    _call("ccd_colsum_f32", _p(_chk(x, torch.float32)), _p(out_zeroed), x.shape[0], x.shape[1], _s())
+    return out_zeroed
+
+
+def l2norm_fwd(x):
+    rows, cols = x.shape
+    y = torch.empty(rows, cols, dtype=torch.bfloat16, device=x.device)
+    inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _call("ccd_l2norm_fwd", _p(_chk(x, torch.float32)), _p(y), _p(inv), rows, cols, _s())
+    return y, inv
+
+
+def l2norm_bwd(x, inv, dy):
+    rows, cols = x.shape
+    dx = torch.empty(rows, cols, dtype=torch.bfloat16, device=x.device)
+    _call("ccd_l2norm_bwd", _p(x), _p(inv), _p(_chk(dy, torch.float32)), _p(dx), rows, cols, _s())
+    return dx
+
+
+def weightnorm_fwd(v, g, w_bf16=None):
+    rows, cols = v.shape
+    if w_bf16 is None:
+        w_bf16 = torch.empty(rows, cols, dtype=torch.bfloat16, device=v.device)
+    inv = torch.empty(rows, dtype=torch.float32, device=v.device)
+    _call("ccd_weightnorm_fwd", _p(_chk(v, torch.float32)), _p(g), _p(w_bf16), _p(inv), rows, cols, _s())
+    return w_bf16, inv
+
+
+def weightnorm_bwd(dw, v, g, inv):
+    rows, cols = v.shape
+    dv = torch.empty_like(v)
+    dg = torch.empty(rows, 1, dtype=torch.float32, device=v.device)
+    _call("ccd_weightnorm_bwd", _p(_chk(dw, torch.float32)), _p(v), _p(g), _p(inv), _p(dv), _p(dg), rows, cols, _s())
+    return dv, dg
+
+
+def cast_bf16(src, dst=None):
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _call("ccd_cast_f32_bf16", _p(_chk(src, torch.float32)), _p(dst), src.numel(), _s())
+    return dst
+
+
+class ChunkTable:
+    """Device pointer table for the multi-tensor kernels; rebuilt only when a data_ptr changes."""
+    CHUNK = 1 << 16
+
+    def __init__(self):
+        self.key = None
+        self.table = None
+        self.n = 0
+
+    def get(self, srcs, dsts, dst_itemsize):
+        key = tuple(t.data_ptr() for t in srcs) + tuple(t.data_ptr() for t in dsts)
+        if key != self.key:
+            rows = []
+            for s, d in zip(srcs, dsts):
+                assert s.is_contiguous() and d.is_contiguous() and s.numel() == d.numel()
+                n = s.numel()
+                for o in range(0, n, self.CHUNK):
+                    rows.append((s.data_ptr() + 4 * o, d.data_ptr() + dst_itemsize * o, min(self.CHUNK, n - o)))
+            self.table = torch.tensor(rows, dtype=torch.int64).to(srcs[0].device)
+            self.n = len(rows)
+            self.key = key
+        return self.table, self.n
+
+
+def multi_tensor(op, table, n, a=0.0, b=0.0):
+    _call("ccd_multi_tensor", op, _p(table), n, float(a), float(b), _s())
+
+
+def patch_im2col(x_img):
+    n = x_img.shape[0]
+    cols = torch.empty(n * 256, 64, dtype=torch.bfloat16, device=x_img.device)
+    _call("ccd_patch_im2col", _p(_chk(x_img, torch.float32)), _p(cols), n, _s())
+    return cols
+
+
+# ---- loss ----
+def dino_ce_fwd(zs, zt, center, ts, tt):
+    R2, K = zs.shape
+    row_loss = torch.empty(R2, dtype=torch.float32, device=zs.device)
+    stats = torch.empty(R2, 4, dtype=torch.float32, device=zs.device)
+    loss = torch.empty(1, dtype=torch.float32, device=zs.device)
+    _call("ccd_dino_ce_fwd", _p(_chk(zs, torch.float32)), _p(_chk(zt, torch.float32)), _p(_chk(center, torch.float32)), float(ts),
+          float(tt), _p(row_loss), _p(stats), _p(loss), R2 // 2, K, _s())
+    return loss, stats
+
+
+def dino_ce_bwd(zs, zt, center, stats, gscale, ts, tt):
+    R2, K = zs.shape
+    dz = torch.empty(R2, K, dtype=torch.bfloat16, device=zs.device)
+    _call("ccd_dino_ce_bwd", _p(zs), _p(zt), _p(center), _p(stats), _p(gscale), float(ts), float(tt), _p(dz), R2 // 2, K, _s())
+    return dz
+
+
+def seg_ce_fwd(logits, gt):
+    n = logits.shape[0]
+    hw = logits.shape[2] * logits.shape[3]
+    ws = torch.empty(296, dtype=torch.float32, device=logits.device)
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    _call("ccd_seg_ce_fwd", _p(_chk(logits, torch.float32)), _p(_chk(gt, torch.float32)), _p(ws), _p(loss), n, hw, _s())
+    return loss
+
+
+def seg_ce_bwd(logits, gt, gscale):
+    d = torch.empty_like(logits)
+    n = logits.shape[0]
+    hw = logits.shape[2] * logits.shape[3]
+    _call("ccd_seg_ce_bwd", _p(logits), _p(gt), _p(gscale), _p(d), n, hw, _s())
+    return d
+
+
+def center_update(center, teacher_logits, world_size, momentum, all_reduce=None):
+    """DINOLoss.update_center (Dino/loss/Dino_loss.py:133-143) incl. the local_rows*world divisor."""
+    K = teacher_logits.shape[1]
+    s = torch.zeros(K, dtype=torch.float32, device=teacher_logits.device)
+    colsum_f32(teacher_logits, s)
+    if all_reduce is not None:
+        all_reduce(s)
+    _call("ccd_center_ema", _p(center), _p(s), float(teacher_logits.shape[0] * world_size), float(momentum), K, _s())
+
+
+# ---- character segments ----
+def ccl_label(src, mode, n_img, want_compact=False):
+    dev = src.device
+    bits = torch.empty(n_img, 32, 128, dtype=torch.int32, device=dev)
+    compact = torch.empty(n_img, 32, 128, dtype=torch.uint8, device=dev) if want_compact else None
+    ncomp = torch.empty(n_img, dtype=torch.int32, device=dev)
+    _call("ccd_ccl_label", _p(_chk(src, torch.float32)), mode, _p(bits), _p(compact), _p(ncomp), n_img, _s())
+    return bits, compact, ncomp
+
+
+def warp_bits(bits, theta):
+    out = torch.empty_like(bits)
+    _call("ccd_warp_bits", _p(bits), _p(_chk(theta, torch.float32)), _p(out), bits.shape[0], _s())
+    return out
+
+
+def warp_mask(mask, theta):
+    out = torch.empty_like(mask)
+    _call("ccd_warp_mask", _p(_chk(mask, torch.float32)), _p(_chk(theta, torch.float32)), _p(out), mask.shape[0], _s())
+    return out
+
+
+def bits_to_dense(bits):
+    n = bits.shape[0]
+    dense = torch.empty(n, SLOTS, 32, 128, dtype=torch.float32, device=bits.device)
+    _call("ccd_bits_to_dense", _p(bits), _p(dense), n, _s())
+    return dense
+
+
+def dense_to_bits(dense):
+    n = dense.shape[0]
+    bits = torch.empty(n, 32, 128, dtype=torch.int32, device=dense.device)
+    _call("ccd_dense_to_bits", _p(_chk(dense, torch.float32)), _p(bits), n, _s())
+    return bits
+
+
+def char_plan(bits):
+    n_view = bits.shape[0] // 2
+    dev = bits.device
+    tot4 = torch.empty(2 * n_view, SLOTS, dtype=torch.int32, device=dev)
+    cnt = torch.empty(n_view, dtype=torch.int32, device=dev)
+    offs = torch.empty(n_view + 1, dtype=torch.int32, device=dev)
+    new_index = torch.empty(n_view, SLOTS, dtype=torch.uint8, device=dev)
+    _call("ccd_char_plan", _p(bits), _p(tot4), _p(cnt), _p(offs), _p(new_index), n_view, _s())
+    return tot4, cnt, offs, new_index
+
+
+def char_pool_fwd(tokens, bits, tot4, cnt, offs, R):
+    n_view = bits.shape[0] // 2
+    E = tokens.shape[-1]
+    rows = torch.empty(2 * R, E, dtype=torch.float32, device=tokens.device)
+    _call("ccd_char_pool_fwd", _p(tokens), 1 if tokens.dtype == torch.bfloat16 else 0, _p(bits), _p(tot4), _p(cnt), _p(offs),
+          _p(rows), n_view, E, _s())
+    return rows
+
+
+def char_pool_bwd(drows, bits, tot4, cnt, offs, E):
+    n_view = bits.shape[0] // 2
+    dtok = torch.empty(2 * n_view * 256, E, dtype=torch.float32, device=drows.device)
+    _call("ccd_char_pool_bwd", _p(_chk(drows, torch.float32)), _p(bits), _p(tot4), _p(cnt), _p(offs), _p(dtok), n_view, E, _s())
+    return dtok

@@ -1,0 +1,112 @@
+/* ccd_b200 -- C ABI of the B200-native (sm_100a) kernels behind the CCD pretraining hot path.
+ *
+ * The reference (TongkunGuan/CCD) has no FFI layer: its "plugin boundary" is the Python module surface that
+ * train.py:27-35 imports (Dino.model.dino_vision.ABIDINOModel, Dino.loss.Dino_loss.DINOLoss, ...).  The drop-in
+ * Python modules of this repository (Dino/, ccd_b200/) call ONLY the entry points declared here, through ctypes
+ * (ccd_b200/lib.py).  Each entry point names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain pointers to DEVICE memory + sizes, a cudaStream_t passed as void*; no allocation, no host
+ * synchronisation, no global state besides cached TMA descriptors / kernel attributes; re-entrant per stream.
+ * Return 0 on success, negative on error (CCD_ERR_*); the Python side turns non-zero into RuntimeError.
+ * bf16 = __nv_bfloat16 storage; all matrices row-major.
+ */
+#ifndef CCD_B200_H
+#define CCD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCD_OK 0
+#define CCD_ERR_ARG (-1)
+#define CCD_ERR_CUDA (-2)
+#define CCD_ERR_TMAP (-3)
+#define CCD_ERR_UNSUPPORTED (-4)
+
+/* ---- GEMM epilogues (ccd_gemm_bf16 `epi`) ---- */
+#define CCD_EPI_BF16 0  /* out0 bf16 = acc + bias                                                   */
+#define CCD_EPI_GELU 1  /* out0 bf16 = acc + bias ; out1 bf16 = gelu_erf(out0)     (Mlp.fc1+act, vision_transformer.py:59-61) */
+#define CCD_EPI_RESID 2 /* out0 f32 = aux_f32 + acc + bias                          (x = x + f(x), vision_transformer.py:109-110) */
+#define CCD_EPI_F32 3   /* out0 f32 = acc + bias ; split-K slices accumulate atomically (caller zero-fills)  */
+#define CCD_EPI_DGELU 4 /* out0 bf16 = acc * gelu'(aux_bf16)                        (autograd of nn.GELU)   */
+#define CCD_EPI_POS 5   /* out0 f32 = acc + bias + aux_f32[(m % 256), :]            (prepare_tokens, vision_transformer.py:225-236) */
+
+/* tcgen05/TMEM/TMA GEMM: C[M,N] = A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulate.
+ * a_mn / b_mn = 0: operand stored [rows, K] (K contiguous); = 1: operand stored [K, rows] (read transposed, no copy).
+ * Replaces every nn.Linear / Conv2d(k=s=4) contraction and its autograd on the path:
+ *   PatchEmbed.proj  vision_transformer.py:126-131 ; Attention.qkv/.proj :82,:90 ; Mlp.fc1/.fc2 :59-65 ;
+ *   DINOHead.mlp / last_layer :324-328.   N % 8 == 0; K-extent leading dims % 8 == 0; pointers 16-byte aligned. */
+int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, int a_mn, int b_mn, int epi, const float* bias,
+                  void* out0, void* out1, const void* aux, int ldc, int splits, void* stream);
+
+/* Fused MHSA forward: qkv bf16 [S*256, 3*H*64] (fused Attention.qkv output) -> out bf16 [S*256, H*64],
+ * lse2 f32 [S,H,256] (log2-domain row log-sum-exp, for backward; may be NULL).  variant 0: P kept in TMEM,
+ * variant 1: P staged through shared memory.  Replaces Attention.forward core, vision_transformer.py:85-89. */
+int ccd_mhsa_fwd(const void* qkv, void* out, float* lse2, int S, int H, int variant, void* stream);
+
+/* Fused MHSA backward: -> dqkv bf16 [S*256, 3*H*64].  Replaces autograd of vision_transformer.py:85-89. */
+int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int S, int H, void* stream);
+
+/* LayerNorm (eps 1e-6) over f32 rows -> bf16 and/or f32.  Block.norm1/norm2, norm, norm_seg: vision_transformer.py:108-110,247,250 */
+int ccd_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, int rows, int E,
+                      float eps, void* stream);
+/* dx = LN'(dy) + resid; writes f32 and/or bf16; dgamma/dbeta accumulate (caller zero-fills). */
+int ccd_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_is_bf16, const float* resid, float* dx_f32,
+                      void* dx_bf16, float* dgamma, float* dbeta, int rows, int E, float eps, void* stream);
+
+/* out[c] += sum_r x[r,c]  (bias gradients / teacher-centre batch sum Dino/loss/Dino_loss.py:138); out zero-filled by caller */
+int ccd_colsum_bf16(const void* x, float* out, int rows, int cols, void* stream);
+int ccd_colsum_f32(const float* x, float* out, int rows, int cols, void* stream);
+
+/* F.normalize(dim=-1) (vision_transformer.py:326) and weight_norm of last_layer (:313-316) */
+int ccd_l2norm_fwd(const float* x, void* y_bf16, float* inv_norm, int rows, int cols, void* stream);
+int ccd_l2norm_bwd(const float* x, const float* inv_norm, const float* dy, void* dx_bf16, int rows, int cols, void* stream);
+int ccd_weightnorm_fwd(const float* v, const float* g, void* w_bf16, float* inv_norm, int rows, int cols, void* stream);
+int ccd_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv, float* dg, int rows,
+                       int cols, void* stream);
+
+/* multi-tensor ops over a device chunk table int64[n_chunks][3] = (src_ptr, dst_ptr, n_elems):
+ * op 0: dst_bf16 = src_f32 ; op 1: dst = a*dst + b*src (teacher EMA, train.py:264-272) ; op 2: dst = a*src */
+int ccd_multi_tensor(int op, const void* table_dev, int n_chunks, float a, float b, void* stream);
+int ccd_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* center = center*m + (sum/denom)*(1-m)   (DINOLoss.update_center, Dino/loss/Dino_loss.py:140-143) */
+int ccd_center_ema(float* center, const float* sum, float denom, float momentum, int n, void* stream);
+/* x f32 [N,3,32,128] -> bf16 [N*256, 64] patch columns (k = c*16+ky*4+kx, zero padded 48..63) */
+int ccd_patch_im2col(const float* x, void* cols_bf16, int n_img, void* stream);
+
+/* DINO cross-view distillation CE (DINOLoss.forward, Dino/loss/Dino_loss.py:81-105).  zs/zt f32 [2R,K];
+ * row_loss [2R], stats [2R,4], loss_out[1] = mean over the 2R cross-view pairs. */
+int ccd_dino_ce_fwd(const float* zs, const float* zt, const float* center, float student_temp, float teacher_temp,
+                    float* row_loss, float* stats, float* loss_out, int R, int K, void* stream);
+int ccd_dino_ce_bwd(const float* zs, const float* zt, const float* center, const float* stats, const float* gscale_dev,
+                    float student_temp, float teacher_temp, void* dz_bf16, int R, int K, void* stream);
+/* Segmentation CE on softmaxed probabilities (Dino_loss.py:63-68,15-26).  logits f32 [N,2,hw], gt f32 [N,hw];
+ * partial_ws >= 296 floats. */
+int ccd_seg_ce_fwd(const float* logits, const float* gt, float* partial_ws, float* loss_out, int n_img, int hw, void* stream);
+int ccd_seg_ce_bwd(const float* logits, const float* gt, const float* gscale_dev, float* dlogits, int n_img, int hw, void* stream);
+
+/* Connected-component character segments (label_cluster.forward, Dino/utils/DBSCAN.py:61-103; loop dino_vision.py:59-71).
+ * mode 0: src = f32 masks [n,32,128]; mode 1: src = f32 seg logits [*,2,32,128] (foreground = logit1 > logit0).
+ * bits u32 [n,32,128] (bit s = slot s) and/or compact u8 [n,32,128] (slot+1, 0 = background); n_comp int[n]. */
+int ccd_ccl_label(const float* src, int mode, void* bits_u32, void* compact_u8, int* n_comp, int n_img, void* stream);
+/* affine_grid + bilinear grid_sample(zeros, align_corners=False) + (> 0.1): dino_vision.py:72-77, train.py:234-236 */
+int ccd_warp_bits(const void* src_bits, const float* theta, void* dst_bits, int n_img, void* stream);
+int ccd_warp_mask(const float* src, const float* theta, float* dst, int n_img, void* stream);
+int ccd_bits_to_dense(const void* bits, float* dense, int n_img, void* stream);
+int ccd_dense_to_bits(const float* dense, void* bits, int n_img, void* stream);
+/* pooling plan: tot4 int[2n,26], cnt int[n], offs int[n+1] (offs[n] = rows per view R), new_index u8 [n,26]
+ * (ragged select, dino_vision.py:82-87) */
+int ccd_char_plan(const void* bits, int* tot4, int* cnt, int* offs, void* new_index_u8, int n_view, void* stream);
+/* mask-guided character pooling (ABIDINOModel.attention, dino_vision.py:38-49) writing only the selected rows [2R,E] */
+int ccd_char_pool_fwd(const void* tokens, int tokens_bf16, const void* bits, const int* tot4, const int* cnt, const int* offs,
+                      float* rows, int n_view, int E, void* stream);
+int ccd_char_pool_bwd(const float* drows, const void* bits, const int* tot4, const int* cnt, const int* offs, float* dtokens,
+                      int n_view, int E, void* stream);
+
+/* library identification (build sanity) */
+int ccd_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCD_B200_H */
