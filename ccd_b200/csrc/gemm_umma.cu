@@ -39,6 +39,8 @@ struct GemmParams {
   const void* aux;
   int ldc;               // leading dim (elements) of out0/out1/aux
   int atomic;            // EPI_F32: accumulate with atomicAdd
+  const float* seq_scale;  // EPI_RESID only: per-sequence (row / 256) scale of the branch (DropPath,
+                           // vision_transformer.py:27-36); null = 1
 };
 
 constexpr int GEMM_BM = 128;
@@ -92,6 +94,11 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
       const float* r = reinterpret_cast<const float*>(p.aux) + off + g * 8;
       const float4 r0 = *reinterpret_cast<const float4*>(r);
       const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
+      if (p.seq_scale != nullptr) {
+        const float sc = __ldg(p.seq_scale + (row >> 8));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= sc;
+      }
       float* o = reinterpret_cast<float*>(p.out0) + off + g * 8;
       *reinterpret_cast<float4*>(o) = make_float4(v[0] + r0.x, v[1] + r0.y, v[2] + r0.z, v[3] + r0.w);
       *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + r1.x, v[5] + r1.y, v[6] + r1.z, v[7] + r1.w);
@@ -264,8 +271,8 @@ using namespace ccd;
 
 // C ABI -- see include/ccd_b200.h
 extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, int a_mn, int b_mn, int epi,
-                             const float* bias, void* out0, void* out1, const void* aux, int ldc, int splits,
-                             void* stream_) {
+                             const float* bias, void* out0, void* out1, const void* aux, const float* seq_scale,
+                             int ldc, int splits, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || epi < 0 || epi >= EPI_COUNT || !A || !B || !out0) return CCD_ERR_ARG;
   if (ldc <= 0) ldc = N;
@@ -292,6 +299,7 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0; p.kb_per_split = kb_per;
   p.bias = bias; p.out0 = out0; p.out1 = out1; p.aux = aux; p.ldc = ldc; p.atomic = (splits > 1) ? 1 : 0;
+  p.seq_scale = seq_scale;
   switch (epi) {
     case EPI_BF16:  return launch_gemm<EPI_BF16, BN>(tmA, tmB, p, splits, stream);
     case EPI_GELU:  return launch_gemm<EPI_GELU, BN>(tmA, tmB, p, splits, stream);

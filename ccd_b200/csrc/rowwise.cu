@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const void* __restrict__ dy_, const float* __restrict__ resid,
                                                             float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            int rows, int E, float eps) {
+                                                            const float* __restrict__ bf16_seq_scale, int rows, int E,
+                                                            float eps) {
   __shared__ float s_dg[512], s_db[512];
   for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
@@ -138,8 +139,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         if (dx_f32) reinterpret_cast<float4*>(dx_f32 + (size_t)row * E)[c] = o;
-        if (dx_bf16)
-          reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * E)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        if (dx_bf16) {
+          // the bf16 copy feeds the NEXT residual branch's grads; DropPath scales that branch per sequence
+          const float sc = bf16_seq_scale ? __ldg(bf16_seq_scale + (row >> 8)) : 1.0f;
+          reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * E)[c] =
+              make_uint2(pack_bf16x2(o.x * sc, o.y * sc), pack_bf16x2(o.z * sc, o.w * sc));
+        }
       }
     }
   }
@@ -339,17 +344,17 @@ extern "C" int ccd_layernorm_fwd(const float* x, const float* gamma, const float
 }
 
 extern "C" int ccd_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_is_bf16, const float* resid,
-                                 float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int rows, int E, float eps,
-                                 void* stream) {
+                                 float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, const float* bf16_seq_scale,
+                                 int rows, int E, float eps, void* stream) {
   if (!x || !gamma || !dy || !dgamma || !dbeta || rows <= 0 || (E & 3) || E > 512) return CCD_ERR_ARG;
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (dy_is_bf16)
     layernorm_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma,
-                                                                          dbeta, rows, E, eps);
+                                                                          dbeta, bf16_seq_scale, rows, E, eps);
   else
     layernorm_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma,
-                                                                           dbeta, rows, E, eps);
+                                                                           dbeta, bf16_seq_scale, rows, E, eps);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }

@@ -67,9 +67,11 @@ def _chk(t, dtype):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def gemm(A, B, M, N, K, a_mn=0, b_mn=0, epi=EPI_BF16, bias=None, out0=None, out1=None, aux=None, ldc=0, splits=1):
+def gemm(A, B, M, N, K, a_mn=0, b_mn=0, epi=EPI_BF16, bias=None, out0=None, out1=None, aux=None, ldc=0, splits=1,
+         seq_scale=None):
     """C[M,N] = A[M,K] B[N,K]^T on tcgen05.  See include/ccd_b200.h:ccd_gemm_bf16."""
-    _call("ccd_gemm_bf16", _p(A), _p(B), M, N, K, a_mn, b_mn, epi, _p(bias), _p(out0), _p(out1), _p(aux), ldc, splits, _s())
+    _call("ccd_gemm_bf16", _p(A), _p(B), M, N, K, a_mn, b_mn, epi, _p(bias), _p(out0), _p(out1), _p(aux), _p(seq_scale), ldc,
+          splits, _s())
     return out0
 
 
@@ -79,11 +81,11 @@ def wgrad_splits(n_out, k_in, t_rows):
     return max(1, min(kb, (296 + tiles - 1) // tiles))
 
 
-def linear_fwd(x_bf16, w_bf16, bias, epi, out0, out1=None, aux=None):
+def linear_fwd(x_bf16, w_bf16, bias, epi, out0, out1=None, aux=None, seq_scale=None):
     """x [T,K] bf16, w [N,K] bf16 (nn.Linear layout)."""
     T, K = x_bf16.shape
     N = w_bf16.shape[0]
-    return gemm(x_bf16, w_bf16, T, N, K, 0, 0, epi, bias, out0, out1, aux)
+    return gemm(x_bf16, w_bf16, T, N, K, 0, 0, epi, bias, out0, out1, aux, seq_scale=seq_scale)
 
 
 def linear_dgrad(dy_bf16, w_bf16, epi, out0, aux=None):
@@ -123,13 +125,13 @@ def layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=False):
     return yb, yf
 
 
-def layernorm_bwd(x, gamma, dy, resid, dgamma, dbeta, want_f32=True, want_bf16=True):
+def layernorm_bwd(x, gamma, dy, resid, dgamma, dbeta, want_f32=True, want_bf16=True, bf16_seq_scale=None):
     rows, E = x.shape
     assert dy.is_contiguous() and dy.shape == x.shape
     dxf = torch.empty(rows, E, dtype=torch.float32, device=x.device) if want_f32 else None
     dxb = torch.empty(rows, E, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     _call("ccd_layernorm_bwd", _p(x), _p(gamma), _p(dy), 1 if dy.dtype == torch.bfloat16 else 0, _p(resid), _p(dxf), _p(dxb),
-          _p(dgamma), _p(dbeta), rows, E, LN_EPS, _s())
+          _p(dgamma), _p(dbeta), _p(bf16_seq_scale), rows, E, LN_EPS, _s())
     return dxf, dxb
 
 

@@ -26,7 +26,7 @@ extern "C" {
 /* ---- GEMM epilogues (ccd_gemm_bf16 `epi`) ---- */
 #define CCD_EPI_BF16 0  /* out0 bf16 = acc + bias                                                   */
 #define CCD_EPI_GELU 1  /* out0 bf16 = acc + bias ; out1 bf16 = gelu_erf(out0)     (Mlp.fc1+act, vision_transformer.py:59-61) */
-#define CCD_EPI_RESID 2 /* out0 f32 = aux_f32 + acc + bias                          (x = x + f(x), vision_transformer.py:109-110) */
+#define CCD_EPI_RESID 2 /* out0 f32 = aux_f32 + s[m/256]*(acc + bias); s = DropPath keep-scale (vision_transformer.py:27-36) or NULL;                         (x = x + f(x), vision_transformer.py:109-110) */
 #define CCD_EPI_F32 3   /* out0 f32 = acc + bias ; split-K slices accumulate atomically (caller zero-fills)  */
 #define CCD_EPI_DGELU 4 /* out0 bf16 = acc * gelu'(aux_bf16)                        (autograd of nn.GELU)   */
 #define CCD_EPI_POS 5   /* out0 f32 = acc + bias + aux_f32[(m % 256), :]            (prepare_tokens, vision_transformer.py:225-236) */
@@ -37,7 +37,7 @@ extern "C" {
  *   PatchEmbed.proj  vision_transformer.py:126-131 ; Attention.qkv/.proj :82,:90 ; Mlp.fc1/.fc2 :59-65 ;
  *   DINOHead.mlp / last_layer :324-328.   N % 8 == 0; K-extent leading dims % 8 == 0; pointers 16-byte aligned. */
 int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, int a_mn, int b_mn, int epi, const float* bias,
-                  void* out0, void* out1, const void* aux, int ldc, int splits, void* stream);
+                  void* out0, void* out1, const void* aux, const float* seq_scale, int ldc, int splits, void* stream);
 
 /* Fused MHSA forward: qkv bf16 [S*256, 3*H*64] (fused Attention.qkv output) -> out bf16 [S*256, H*64],
  * lse2 f32 [S,H,256] (log2-domain row log-sum-exp, for backward; may be NULL).  variant 0: P kept in TMEM,
@@ -52,7 +52,8 @@ int ccd_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
                       float eps, void* stream);
 /* dx = LN'(dy) + resid; writes f32 and/or bf16; dgamma/dbeta accumulate (caller zero-fills). */
 int ccd_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_is_bf16, const float* resid, float* dx_f32,
-                      void* dx_bf16, float* dgamma, float* dbeta, int rows, int E, float eps, void* stream);
+                      void* dx_bf16, float* dgamma, float* dbeta, const float* bf16_seq_scale, int rows, int E, float eps,
+                      void* stream);
 
 /* out[c] += sum_r x[r,c]  (bias gradients / teacher-centre batch sum Dino/loss/Dino_loss.py:138); out zero-filled by caller */
 int ccd_colsum_bf16(const void* x, float* out, int rows, int cols, void* stream);

@@ -89,7 +89,11 @@ def load_reference():
     # our own repo ships a `Dino` drop-in package: make sure the reference's wins for this process
     for k in [k for k in sys.modules if k == "Dino" or k.startswith("Dino.")]:
         del sys.modules[k]
-    sys.path.insert(0, REFERENCE_ROOT)
+    # the reference's Dino/ has no __init__.py (namespace package): a regular `Dino` package anywhere on sys.path
+    # (this repository's drop-in) would win over it, so hide those entries while the reference is imported
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [e for e in saved_path
+                                      if not os.path.isfile(os.path.join(e or os.getcwd(), "Dino", "__init__.py"))]
     try:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -100,7 +104,7 @@ def load_reference():
             mutils = importlib.import_module("Dino.modules.utils")
             dbscan = importlib.import_module("Dino.utils.DBSCAN")
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path[:] = saved_path
         ref_mods = {k: v for k, v in sys.modules.items() if k == "Dino" or k.startswith("Dino.")}
         for k in ref_mods:
             del sys.modules[k]
