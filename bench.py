@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""CCD pretraining throughput benchmark (BASELINE.json metric: pretrain images/sec, ViT-Small, 3x32x128 crops).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's sm_100a path
+    python bench.py --impl reference ...                      # the reference algorithm's CPU path (oracle port) on host cores
+
+One "step" = one full pretraining step of train.py:221-275 on one synthetic batch:
+student fwd + teacher fwd + DINO/seg loss + backward (+DDP all-reduce) + per-parameter clip + AdamW + teacher EMA +
+centre update, at ViT-Small, batch 256 per GPU, bf16 tensor-core operands / fp32 accumulate, drop_path 0.1, out_dim 65536,
+2 views (the reference forwards exactly two views -- SURVEY.md F1/N1; "local crops" have no reference semantics).
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same step fed from pinned
+host memory (H2D inside the timed region) with a device->host read of the loss every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CCD pretrain images/sec (ViT-Small, 3x32x128)"
+ARCH_DIMS = {"vit_tiny": 192, "vit_small": 384, "vit_base": 512}
+
+
+def f_sample(E, rbar=8.5):
+    """Algorithmic FLOPs per image."""
+    f_vit = 2 * 256 * 48 * E + 12 * (6 * 256 * E * E + 4 * (E // 64) * 256 * 256 * 64 + 2 * 256 * E * E + 16 * 256 * E * E)
+    f_head = 2 * (E * 2048 + 2048 * 2048 + 2048 * 256 + 256 * 65536)
+    f_seg = 3 * (2 * 256 * E * 9 * 128 + 2 * 256 * 128 * 64) + 2 * 256 * 192 * 128 * 16 + 2 * 1024 * 128 * 128 * 16 + 2 * 4096 * 128 * 9 * 2
+    return 8 * f_vit + 8 * rbar * f_head + 6 * f_seg
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(args, as_line):
+    """The reference algorithm's own CPU path (oracle/ccd_oracle.py, pinned against the unmodified reference) on the host
+    cores of this box: fwd + loss + bwd of one synthetic batch, fp32, all threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ccd_oracle as O
+    from ccd_b200 import synthetic as S
+    from ccd_b200.encoder import vit_small
+    from ccd_b200.head import DINOHead
+    from ccd_b200.model import ABIDINOModel
+    from ccd_b200.segmentor import SegHead
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.cpu_batch
+    torch.manual_seed(0)
+    shapes_s = {k: v.shape for k, v in ABIDINOModel(vit_small(patch_size=4), SegHead(in_channels=384), DINOHead(384, 65536)).state_dict().items()}
+    shapes_t = {k: v for k, v in shapes_s.items() if not k.startswith("segmentation.")}
+    ssd = {k: v.requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in S.fill_state_dict(shapes_s, 0).items()}
+    tsd = S.fill_state_dict(shapes_t, 0)
+    x, masks, metrics = S.make_batch(B, seed=1234)
+    center = torch.zeros(1, 65536)
+    steps, warm = (args.steps, args.warmup) if as_line else (2, 1)
+    times = []
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        L, parts = O.pretrain_loss(ssd, tsd, "vit_small", x, metrics, masks, center, 0, 0.04)
+        L.backward()
+        for v in ssd.values():
+            v.grad = None
+        center = parts["center"].detach()
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    cb = {"value": B / sec, "unit": "images/s", "cores": cores, "kind": "port",
+          "sample": f"oracle (fp32 torch restatement of the reference) ViT-Small fwd+loss+bwd, batch {B}, out_dim 65536, "
+                    f"{len(times)} timed step(s) of {sec:.2f} s"}
+    if not as_line:
+        return cb
+    line = {"metric": METRIC, "value": B / sec, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "ViT-Small CCD pretrain step (2 views, out_dim 65536), bounded CPU sample", "batch": B},
+            "cpu_baseline": cb, "e2e": {"value": B / sec, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ccd_b200", choices=["ccd_b200", "reference"])
+    ap.add_argument("--arch", default="vit_small")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--out-dim", type=int, default=65536)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write per-shape GEMM/attention timings (json)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            cpu_reference_arm(args, as_line=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ccd_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    from ccd_b200 import ops, synthetic as S
+    from ccd_b200.trainer import PretrainStep
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ddp = world > 1
+    if ddp:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = args.steps
+    B = args.batch
+    trainer = PretrainStep(arch=args.arch, out_dim=args.out_dim, batch_per_gpu=B, drop_path_rate=0.1, device=dev, ddp=ddp)
+    trainer.student.train()
+    x_h, m_h, t_h = S.make_batch(B, seed=1234 + rank)
+    x_h, m_h, t_h = x_h.pin_memory(), m_h.pin_memory(), t_h.pin_memory()
+    x_d, m_d, t_d = x_h.to(dev), m_h.to(dev), t_h.to(dev)
+    # L2 flush between timed iterations is implicit: one step streams > 20 GB of activations through a 126 MB L2
+    def barrier():
+        if ddp:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        trainer.step(x_d, m_d, t_d, sync_loss=False)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE = {"names": {"ccd_gemm_bf16", "ccd_mhsa_fwd", "ccd_mhsa_bwd"}, "events": []}
+    l0 = ops.LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        loss = trainer.step(x_d, m_d, t_d, sync_loss=False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES[0] - l0
+    prof, ops.PROFILE = ops.PROFILE, None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if ddp:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    final_loss = loss.item()
+
+    # ---- timed region 2: end to end from pinned host memory, loss read back every step ----
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        e0.record()
+        for _ in range(K):
+            trainer.step(x_h, m_h, t_h, sync_loss=True)          # H2D copies + loss.item() inside
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if ddp:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d = (x_h.numel() + m_h.numel() + t_h.numel()) * 4
+        e2e = {"value": B * world * K / (t.item() / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": 4 * world}
+
+    if rank != 0:
+        if ddp:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), measured live over timed region 1 ----
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    agg = {}
+    for name, work, a, b in prof["events"]:
+        d = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "n": 0, "shapes": {}})
+        dt = a.elapsed_time(b)
+        d["ms"] += dt; d["flops"] += work[0]; d["n"] += 1
+        sh = d["shapes"].setdefault(str(work[1]), [0.0, 0.0, 0])
+        sh[0] += dt; sh[1] += work[0]; sh[2] += 1
+    gemm = agg.get("ccd_gemm_bf16", {"ms": 1e-9, "flops": 0.0, "n": 1})
+    ach = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_umma_kernel (tcgen05 GEMM, all linear contractions fwd+bwd)", "bound": "tensor",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": peak_src, "launches": gemm["n"], "avg_launch_ms": gemm["ms"] / max(1, gemm["n"]),
+                "share_of_step": gemm["ms"] / ms,
+                "other": {k: {"ms_per_step": v["ms"] / K, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "launches": v["n"]}
+                          for k, v in agg.items()}}
+    if args.profile_out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+        with open(args.profile_out, "w") as f:
+            json.dump({k: {"ms_per_step": v["ms"] / K,
+                           "shapes": {s: {"ms_per_step": x[0] / K, "tflops": x[1] / (x[0] * 1e-3) / 1e12, "calls_per_step": x[2] / K}
+                                      for s, x in v["shapes"].items()}} for k, v in agg.items()}, f, indent=1)
+    E = ARCH_DIMS[args.arch]
+    value = B * world * K / (ms / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.arch} CCD pretrain step, batch {B}/GPU, 2 views (reference semantics), out_dim {args.out_dim}, "
+                               "drop_path 0.1, fwd+bwd+clip+AdamW+EMA+centre", "arch": args.arch, "global_batch": B * world,
+                   "parallelism": f"dp{world}", "l2": "inputs+activations >> L2 (20+ GB streamed per step)",
+                   "seg_head": "cuDNN (torch) convs in round 1"},
+        "step_tensor_util": f_sample(E) * value / world / (peak_tf * 1e12),
+        "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "loss": final_loss,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_arm(args, as_line=False)
+    print(json.dumps(line))
+    if ddp:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -16,7 +16,11 @@ SLOTS = 26
 
 _CTYPE = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong}
 _FN = {}
-LAUNCHES = [0]     # number of kernel-launching C-ABI calls (bench.py reports it)
+LAUNCHES = [0]     # number of kernels launched through the C ABI (bench.py reports it)
+KERNELS_PER_CALL = {"ccd_dino_ce_fwd": 2, "ccd_seg_ce_fwd": 2, "ccd_char_plan": 3}
+# bench.py roofline instrumentation: when a dict, every call of a listed entry point is bracketed by CUDA events on
+# the launching stream:  PROFILE = {"names": {"ccd_gemm_bf16", ...}, "events": []}
+PROFILE = None
 
 
 def _bind():
@@ -41,10 +45,18 @@ def _bind():
         _FN[name] = fn
 
 
-def _call(name, *args):
+def _call(name, *args, work=None):
     _bind()
-    rc = _FN[name](*args)
-    LAUNCHES[0] += 1
+    prof = PROFILE
+    if prof is not None and name in prof["names"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = _FN[name](*args)
+        e1.record()
+        prof["events"].append((name, work, e0, e1))
+    else:
+        rc = _FN[name](*args)
+    LAUNCHES[0] += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"{name} failed with code {rc}")
 
@@ -71,7 +83,7 @@ def gemm(A, B, M, N, K, a_mn=0, b_mn=0, epi=EPI_BF16, bias=None, out0=None, out1
          seq_scale=None):
     """C[M,N] = A[M,K] B[N,K]^T on tcgen05.  See include/ccd_b200.h:ccd_gemm_bf16."""
     _call("ccd_gemm_bf16", _p(A), _p(B), M, N, K, a_mn, b_mn, epi, _p(bias), _p(out0), _p(out1), _p(aux), _p(seq_scale), ldc,
-          splits, _s())
+          splits, _s(), work=(2.0 * M * N * K, (M, N, K, a_mn, b_mn, epi)))
     return out0
 
 
@@ -107,13 +119,15 @@ def mhsa_fwd(qkv, S, H, want_lse=True, variant=0):
     E = H * 64
     out = torch.empty(S * 256, E, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(S, H, 256, dtype=torch.float32, device=qkv.device) if want_lse else None
-    _call("ccd_mhsa_fwd", _p(_chk(qkv, torch.bfloat16)), _p(out), _p(lse), S, H, variant, _s())
+    _call("ccd_mhsa_fwd", _p(_chk(qkv, torch.bfloat16)), _p(out), _p(lse), S, H, variant, _s(),
+          work=(4.0 * 256 * 256 * 64 * S * H, (S, H)))
     return out, lse
 
 
 def mhsa_bwd(qkv, o, d_o, lse, S, H):
     dqkv = torch.empty_like(qkv)
-    _call("ccd_mhsa_bwd", _p(qkv), _p(o), _p(_chk(d_o, torch.bfloat16)), _p(lse), _p(dqkv), S, H, _s())
+    _call("ccd_mhsa_bwd", _p(qkv), _p(o), _p(_chk(d_o, torch.bfloat16)), _p(lse), _p(dqkv), S, H, _s(),
+          work=(10.0 * 256 * 256 * 64 * S * H, (S, H)))
     return dqkv
 
 

@@ -1,0 +1,85 @@
+"""One CCD pretraining step, as the reference's train.py:221-275 drives it, on the drop-in modules.
+
+This is caller-side glue (what a user's train.py does around Dino.model / Dino.loss); it exists so that bench.py,
+smoke() and the tests run exactly the step BASELINE.json's metric is quoted on:
+  H2D (optional) -> student fwd -> teacher fwd -> GT-mask warp -> DINOLoss -> backward (+DDP all-reduce)
+  -> per-parameter clip -> cancel last-layer grads (epoch < freeze_last_layer) -> AdamW -> teacher EMA.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from .train_utils import (TeacherEMA, cancel_gradients_last_layer, clip_gradients, cosine_iter_scheduler,
+                          get_params_groups, has_batchnorms)
+
+
+class PretrainStep:
+    def __init__(self, arch="vit_small", out_dim=65536, batch_per_gpu=256, drop_path_rate=0.1, norm_last_layer=False,
+                 lr=0.0005, weight_decay=0.04, weight_decay_end=0.4, clip_grad=3.0, freeze_last_layer=1,
+                 momentum_teacher=0.9995, total_iters=100000, device="cuda", ddp=False, seed=0):
+        from Dino.loss.Dino_loss import DINOLoss
+        from Dino.model.dino_vision import ABIDINOModel
+        from Dino.modules import vision_transformer as vits
+        from Dino.modules.segmentor import SegHead
+        torch.manual_seed(seed)
+        self.device = torch.device(device)
+        student_bb = vits.__dict__[arch](patch_size=4, drop_path_rate=drop_path_rate)        # train.py:63-67
+        teacher_bb = vits.__dict__[arch](patch_size=4)
+        E = student_bb.embed_dim
+        student = ABIDINOModel(student_bb, SegHead(in_channels=E, mla_channels=128, mlahead_channels=64, num_classes=2),
+                               vits.DINOHead(E, out_dim, use_bn=False, norm_last_layer=norm_last_layer))   # :83-86
+        teacher = ABIDINOModel(teacher_bb, None, vits.DINOHead(E, out_dim, False))                            # :87-90
+        student, teacher = student.to(self.device), teacher.to(self.device)
+        self.world = dist.get_world_size() if (ddp and dist.is_initialized()) else 1
+        self.student_module, self.teacher_module = student, teacher
+        if ddp and dist.is_initialized():
+            if has_batchnorms(student):                                                                       # :96-101
+                student = nn.SyncBatchNorm.convert_sync_batchnorm(student)
+                self.student_module = student
+            student = nn.parallel.DistributedDataParallel(student, device_ids=[self.device.index],
+                                                          find_unused_parameters=True)                        # :106
+        self.student, self.teacher = student, teacher
+        teacher.backbone.load_state_dict(self.student_module.backbone.state_dict())                           # :109-110
+        teacher.head.load_state_dict(self.student_module.head.state_dict())
+        for p in teacher.parameters():
+            p.requires_grad = False
+        self.loss = DINOLoss(out_dim, 2, 0.04, 0.04, 0, 101).to(self.device)                                  # :122-129
+        self.opt = torch.optim.AdamW(get_params_groups(student), fused=True)                                  # :131-133
+        glob = batch_per_gpu * self.world
+        self.lr_sched = cosine_iter_scheduler(lr * glob / 256., 1e-6, total_iters,
+                                              warmup_iters=min(total_iters // 10, max(1, int(10 * 1000000 / glob))))
+        self.wd_sched = cosine_iter_scheduler(weight_decay, weight_decay_end, total_iters)
+        self.mom_sched = cosine_iter_scheduler(momentum_teacher, 1, total_iters)
+        self.clip_grad, self.freeze_last_layer = clip_grad, freeze_last_layer
+        self.ema = TeacherEMA(self.student_module, teacher)
+        self.iteration = 0
+        self.batch_per_gpu = batch_per_gpu
+
+    def step(self, image_tensors, masks, metrics, epoch=0, sync_loss=True):
+        it = self.iteration
+        image_tensors = image_tensors.to(self.device, non_blocking=True)                                     # train.py:221-222
+        masks = masks.to(self.device, non_blocking=True)
+        metrics = metrics.to(self.device, non_blocking=True).float()
+        for i, g in enumerate(self.opt.param_groups):                                                         # :224-227
+            g["lr"] = float(self.lr_sched[it])
+            if i == 0:
+                g["weight_decay"] = float(self.wd_sched[it])
+        so = self.student(image_tensors, metrics, masks, epoch, clusters=None)                                # :232
+        to = self.teacher(image_tensors, metrics, None, None, clusters=so["zero"], index=so["index"])         # :233
+        masks_image = ops.warp_mask(masks.contiguous().float(), metrics.contiguous())                         # :234-236
+        so["gt"] = [masks, masks_image]
+        loss = self.loss(so, to, epoch)                                                                       # :238
+        if sync_loss and not math.isfinite(loss.item()):                                                      # :239-241
+            raise FloatingPointError(f"Loss is {loss.item()}, stopping training")
+        self.opt.zero_grad(set_to_none=True)                                                                  # :244
+        loss.backward()                                                                                       # :247
+        if self.clip_grad:
+            clip_gradients(self.student, self.clip_grad)                                                      # :249
+        cancel_gradients_last_layer(epoch, self.student, self.freeze_last_layer)                              # :250
+        self.opt.step()                                                                                       # :252
+        self.ema.step(float(self.mom_sched[it]))                                                              # :264-272
+        self.iteration += 1
+        return loss
