@@ -166,7 +166,7 @@ class VitFn(torch.autograd.Function):
         n = x_img.shape[0]
         T = n * GRID_TOKENS
         dev = x_img.device
-        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        save = any(ctx.needs_input_grad)     # grad mode is off inside Function.forward; this reflects the caller's
         f32 = dict(dtype=torch.float32, device=dev)
         b16 = dict(dtype=torch.bfloat16, device=dev)
         pos_embed, _, patch_b = params[0], params[1], params[2]

@@ -85,7 +85,7 @@ class HeadFn(torch.autograd.Function):
         wn, winv = ops.weightnorm_fwd(wv.detach(), wg.detach(), mod._wn)      # bf16 (g/||v||) v, never an fp32 W
         logits = torch.empty(R2, K, dtype=torch.float32, device=dev)
         ops.linear_fwd(yn, wn, None, ops.EPI_F32, logits)
-        if torch.is_grad_enabled() and any(ctx.needs_input_grad):
+        if any(ctx.needs_input_grad):
             ctx.save_for_backward(xb, p1, a1, p2, a2, h3, yn, inv, wn, winv, wg, wv)
             ctx.wb = wb
             ctx.logits_ptr = logits.data_ptr()
