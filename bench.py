@@ -129,12 +129,57 @@ def cpu_reference_arm(args, as_line):
     print(json.dumps(line))
 
 
+def stock_eager_cuda_arm(args):
+    """INFORMATIONAL baseline (not part of the driver contract): the reference algorithm as stock eager PyTorch on the
+    same GPU -- the oracle restatement (pinned against the unmodified reference) executed on cuda tensors, fp32 as the
+    reference ships (use_fp16: False) or under torch.autocast(bf16); fwd+loss+bwd+AdamW, CPU-side CCL like the reference.
+    BASELINE.md B1 asks for this number; /root/reference itself cannot travel to the GPU box."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ccd_oracle as O
+    from ccd_b200 import synthetic as S
+    from ccd_b200.encoder import vit_small
+    from ccd_b200.head import DINOHead
+    from ccd_b200.model import ABIDINOModel
+    from ccd_b200.segmentor import SegHead
+    dev = torch.device("cuda", 0)
+    B = args.batch
+    shapes_s = {k: v.shape for k, v in ABIDINOModel(vit_small(patch_size=4), SegHead(in_channels=384), DINOHead(384, 65536)).state_dict().items()}
+    shapes_t = {k: v for k, v in shapes_s.items() if not k.startswith("segmentation.")}
+    ssd = {k: v.to(dev).requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in S.fill_state_dict(shapes_s, 0).items()}
+    tsd = {k: v.to(dev) for k, v in S.fill_state_dict(shapes_t, 0).items()}
+    params = [v for v in ssd.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+    x, masks, metrics = [t.to(dev) for t in S.make_batch(B, seed=1234)]
+    center = torch.zeros(1, 65536, device=dev)
+    out = {}
+    for mode in ("fp32", "autocast_bf16"):
+        times = []
+        try:
+            for i in range(args.warmup + args.steps):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode != "fp32")):
+                    L, parts = O.pretrain_loss(ssd, tsd, "vit_small", x, metrics, masks, center, 0, 0.04)
+                opt.zero_grad(set_to_none=True)
+                L.backward()
+                opt.step()
+                center = parts["center"].detach().float()
+                torch.cuda.synchronize()
+                if i >= args.warmup:
+                    times.append(time.perf_counter() - t0)
+            out[mode] = {"images_per_s": B * len(times) / sum(times), "ms_per_step": 1e3 * sum(times) / len(times), "loss": L.item()}
+        except Exception as e:  # e.g. out of memory at fp32 B=256 with the materialised attention matrices
+            out[mode] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    print(json.dumps({"impl": "stock-eager-cuda (informational)", "metric": METRIC, "batch": B, "steps": args.steps, "results": out}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ccd_b200", choices=["ccd_b200", "reference"])
+    ap.add_argument("--impl", default="ccd_b200", choices=["ccd_b200", "reference", "stock-eager-cuda"])
     ap.add_argument("--arch", default="vit_small")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--out-dim", type=int, default=65536)
@@ -150,6 +195,10 @@ def main():
     if args.impl == "reference":
         if rank == 0:
             cpu_reference_arm(args, as_line=True)
+        return
+    if args.impl == "stock-eager-cuda":
+        if rank == 0:
+            stock_eager_cuda_arm(args)
         return
 
     import torch

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) weightnorm_bwd_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------------------
 // multi-tensor kernels over a chunk table: int64 [n_chunks, 3] = (src_ptr, dst_ptr, n_elems <= 65536*?)
 // ---------------------------------------------------------------------------------------------------------
-enum MultiOp { MT_CAST_BF16 = 0, MT_EMA = 1, MT_SCALE = 2 };
+enum MultiOp { MT_CAST_BF16 = 0, MT_EMA = 1, MT_SCALE = 2, MT_SQNORM = 3, MT_CLIP = 4 };
 template <int OP>
 __global__ void __launch_bounds__(256) multi_tensor_kernel(const long long* __restrict__ table, float a, float b) {
   const long long* e = table + (size_t)blockIdx.x * 3;
@@ -289,9 +289,27 @@ __global__ void __launch_bounds__(256) multi_tensor_kernel(const long long* __re
   } else if constexpr (OP == MT_EMA) {   // dst = a*dst + b*src   (teacher EMA, train.py:268-272)
     float* dst = reinterpret_cast<float*>(e[1]);
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = a * dst[i] + b * src[i];
-  } else {                               // dst = a*src
+  } else if constexpr (OP == MT_SCALE) {  // dst = a*src
     float* dst = reinterpret_cast<float*>(e[1]);
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = a * src[i];
+  } else if constexpr (OP == MT_SQNORM) { // *dst += sum(src^2)   (dst = &sqnorm[tensor]; zero-filled by the caller)
+    float* dst = reinterpret_cast<float*>(e[1]);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += src[i] * src[i];
+    __shared__ float sm[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += sm[w];
+      atomicAdd(dst, t);
+    }
+  } else {                                // per-parameter clip (Dino/modules/utils.py:132-141): src = &sqnorm[tensor],
+    float* dst = reinterpret_cast<float*>(e[1]);   // dst = grad chunk; g *= clip/(||g||+1e-6) if that is < 1
+    const float coef = a / (sqrtf(src[0]) + 1e-6f);
+    if (coef < 1.0f)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] *= coef;
   }
 }
 
@@ -412,6 +430,8 @@ extern "C" int ccd_multi_tensor(int op, const void* table_dev, int n_chunks, flo
     case MT_CAST_BF16: multi_tensor_kernel<MT_CAST_BF16><<<n_chunks, 256, 0, s>>>(t, a, b); break;
     case MT_EMA: multi_tensor_kernel<MT_EMA><<<n_chunks, 256, 0, s>>>(t, a, b); break;
     case MT_SCALE: multi_tensor_kernel<MT_SCALE><<<n_chunks, 256, 0, s>>>(t, a, b); break;
+    case MT_SQNORM: multi_tensor_kernel<MT_SQNORM><<<n_chunks, 256, 0, s>>>(t, a, b); break;
+    case MT_CLIP: multi_tensor_kernel<MT_CLIP><<<n_chunks, 256, 0, s>>>(t, a, b); break;
     default: return CCD_ERR_ARG;
   }
   CCD_LAUNCH_CHECK();

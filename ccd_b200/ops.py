@@ -10,7 +10,7 @@ import torch
 from . import lib as _lib
 
 EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32, EPI_DGELU, EPI_POS = 0, 1, 2, 3, 4, 5
-MT_CAST_BF16, MT_EMA, MT_SCALE = 0, 1, 2
+MT_CAST_BF16, MT_EMA, MT_SCALE, MT_SQNORM, MT_CLIP = 0, 1, 2, 3, 4
 LN_EPS = 1e-6
 SLOTS = 26
 
@@ -220,6 +220,42 @@ class ChunkTable:
             self.n = len(rows)
             self.key = key
         return self.table, self.n
+
+
+class ClipTable:
+    """Pointer tables for the multi-tensor per-parameter clip: (grad chunk -> &sqnorm[i]) and (&sqnorm[i] -> grad chunk)."""
+    CHUNK = 1 << 16
+
+    def __init__(self):
+        self.key = None
+
+    def get(self, grads):
+        key = tuple(g.data_ptr() for g in grads)
+        if key != self.key:
+            dev = grads[0].device
+            self.norms = torch.zeros(len(grads), dtype=torch.float32, device=dev)
+            base = self.norms.data_ptr()
+            a, b = [], []
+            for i, g in enumerate(grads):
+                assert g.is_contiguous() and g.dtype == torch.float32
+                for o in range(0, g.numel(), self.CHUNK):
+                    n = min(self.CHUNK, g.numel() - o)
+                    a.append((g.data_ptr() + 4 * o, base + 4 * i, n))
+                    b.append((base + 4 * i, g.data_ptr() + 4 * o, n))
+            self.t_norm = torch.tensor(a, dtype=torch.int64).to(dev)
+            self.t_clip = torch.tensor(b, dtype=torch.int64).to(dev)
+            self.n = len(a)
+            self.key = key
+        return self
+
+
+def clip_per_parameter_(grads, clip, table):
+    """In-place per-parameter L2 clip of a list of fp32 gradient tensors in two launches, no host sync."""
+    t = table.get(grads)
+    t.norms.zero_()
+    multi_tensor(MT_SQNORM, t.t_norm, t.n)
+    multi_tensor(MT_CLIP, t.t_clip, t.n, float(clip))
+    return t.norms
 
 
 def multi_tensor(op, table, n, a=0.0, b=0.0):

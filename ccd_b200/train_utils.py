@@ -13,15 +13,19 @@ import torch.nn as nn
 from . import ops
 
 
+_CLIP_TABLES = {}
+
+
 def clip_gradients(model, clip):
-    """Per-parameter L2 clip (Dino/modules/utils.py:132-141) -- without the reference's per-parameter .item() sync."""
-    norms = []
-    for _, p in model.named_parameters():
-        if p.grad is not None:
-            n = p.grad.data.norm(2)
-            norms.append(n)
-            p.grad.data.mul_(torch.clamp(clip / (n + 1e-6), max=1.0))
-    return norms
+    """Per-parameter L2 clip (Dino/modules/utils.py:132-141).  On CUDA: two multi-tensor launches, no host sync
+    (the reference does one .item() per parameter); returns the squared norms as a device tensor."""
+    grads = [p.grad for _, p in model.named_parameters() if p.grad is not None]
+    if not grads:
+        return []
+    if not all(g.is_cuda and g.is_contiguous() and g.dtype == torch.float32 for g in grads):
+        raise RuntimeError("ccd_b200.clip_gradients needs contiguous fp32 CUDA gradients (there is no CPU path)")
+    table = _CLIP_TABLES.setdefault(id(model), ops.ClipTable())
+    return ops.clip_per_parameter_(grads, clip, table).sqrt()
 
 
 def cancel_gradients_last_layer(epoch, model, freeze_last_layer):

@@ -67,7 +67,8 @@ int ccd_weightnorm_bwd(const float* dw, const float* v, const float* g, const fl
                        int cols, void* stream);
 
 /* multi-tensor ops over a device chunk table int64[n_chunks][3] = (src_ptr, dst_ptr, n_elems):
- * op 0: dst_bf16 = src_f32 ; op 1: dst = a*dst + b*src (teacher EMA, train.py:264-272) ; op 2: dst = a*src */
+ * op 0: dst_bf16 = src_f32 ; op 1: dst = a*dst + b*src (teacher EMA, train.py:264-272) ; op 2: dst = a*src ;
+ * op 3: *dst += sum(src^2) ; op 4: dst *= a/(sqrt(*src)+1e-6) if < 1  (per-parameter clip, Dino/modules/utils.py:132-141) */
 int ccd_multi_tensor(int op, const void* table_dev, int n_chunks, float a, float b, void* stream);
 int ccd_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 /* center = center*m + (sum/denom)*(1-m)   (DINOLoss.update_center, Dino/loss/Dino_loss.py:140-143) */

@@ -362,3 +362,19 @@ def test_patch_im2col(ops):
     want = torch.nn.functional.unfold(x, 4, stride=4).transpose(1, 2).reshape(3 * 256, 48)
     assert torch.equal(cols[:, :48], want.to(torch.bfloat16))
     assert (cols[:, 48:] == 0).all()
+
+
+def test_multi_tensor_clip(ops):
+    import ccd_oracle as O
+    from ccd_b200 import train_utils as U
+    g = torch.Generator(device="cuda").manual_seed(12)
+    lin = torch.nn.Sequential(torch.nn.Linear(300, 400), torch.nn.LayerNorm(400), torch.nn.Linear(400, 3)).cuda()
+    scales = [10.0, 0.001, 0.2, 5.0, 0.5, 0.01]
+    for p, s in zip(lin.parameters(), scales):
+        p.grad = torch.randn(p.shape, device="cuda", generator=g) * s
+    want = O.clip_per_parameter({n: p.grad.clone() for n, p in lin.named_parameters()}, 3.0)
+    norms0 = [p.grad.norm().item() for p in lin.parameters()]
+    norms = U.clip_gradients(lin, 3.0)
+    for (n, p), n0, n1 in zip(lin.named_parameters(), norms0, norms.tolist()):
+        assert abs(n0 - n1) < 1e-3 * n0
+        assert (p.grad - want[n]).abs().max() < 1e-5 * max(1.0, want[n].abs().max().item())

@@ -81,6 +81,13 @@ def test_oracle_step_matches_reference_golden(name):
             assert abs(gr.norm().item() - norm) < 1e-2 * norm + 1e-7, (n, gr.norm().item(), norm)
 
 
+def test_explicit_forms_of_layernorm_and_gelu():
+    x = torch.randn(7, 192, dtype=torch.float64)
+    w, b = torch.randn(192, dtype=torch.float64), torch.randn(192, dtype=torch.float64)
+    assert (O.layer_norm(x, w, b) - O.layer_norm_explicit(x, w, b)).abs().max() < 1e-12
+    assert (O.gelu(x) - O.gelu_explicit(x)).abs().max() < 1e-12
+
+
 def test_clip_ema_schedule_restatements():
     g = {"a": torch.full((10,), 2.0), "b": torch.full((4,), 0.1)}
     c = O.clip_per_parameter(g, 3.0)
