@@ -83,6 +83,20 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Host threads this process may really use: CPU affinity capped by the cgroup CPU quota (a 128-thread OpenMP team on
+    a container limited to a few cores oversubscribes catastrophically)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, min(n, int(os.environ.get("CCD_CPU_THREADS", "64"))))
+
+
 def cpu_reference_arm(args, as_line):
     """The reference algorithm's own CPU path (oracle/ccd_oracle.py, pinned against the unmodified reference) on the host
     cores of this box: fwd + loss + bwd of one synthetic batch, fp32, all threads."""
@@ -94,7 +108,7 @@ def cpu_reference_arm(args, as_line):
     from ccd_b200.head import DINOHead
     from ccd_b200.model import ABIDINOModel
     from ccd_b200.segmentor import SegHead
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     B = args.cpu_batch
     torch.manual_seed(0)
@@ -106,14 +120,18 @@ def cpu_reference_arm(args, as_line):
     center = torch.zeros(1, 65536)
     steps, warm = (args.steps, args.warmup) if as_line else (2, 1)
     times = []
+    budget = float(os.environ.get("CCD_CPU_BUDGET_S", "150" if as_line else "40"))
+    t_begin = time.perf_counter()
     for i in range(warm + steps):
+        if times and time.perf_counter() - t_begin > budget:       # bounded sample: stop once the time budget is spent
+            break
         t0 = time.perf_counter()
         L, parts = O.pretrain_loss(ssd, tsd, "vit_small", x, metrics, masks, center, 0, 0.04)
         L.backward()
         for v in ssd.values():
             v.grad = None
         center = parts["center"].detach()
-        if i >= warm:
+        if i >= warm or (i == warm - 1 and time.perf_counter() - t_begin > budget):
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     cb = {"value": B / sec, "unit": "images/s", "cores": cores, "kind": "port",
@@ -121,7 +139,7 @@ def cpu_reference_arm(args, as_line):
                     f"{len(times)} timed step(s) of {sec:.2f} s"}
     if not as_line:
         return cb
-    line = {"metric": METRIC, "value": B / sec, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+    line = {"metric": METRIC, "value": B / sec, "unit": "images/s", "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": "ViT-Small CCD pretrain step (2 views, out_dim 65536), bounded CPU sample", "batch": B},
@@ -183,7 +201,7 @@ def main():
     ap.add_argument("--arch", default="vit_small")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--out-dim", type=int, default=65536)
-    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write per-shape GEMM/attention timings (json)")

@@ -42,7 +42,7 @@ def run_step(student, teacher, K, B, epoch=0):
     from Dino.loss.Dino_loss import DINOLoss
     from ccd_b200 import ops, synthetic as S
     x, masks, metrics = S.make_batch(B, seed=1234, device="cuda")
-    loss_mod = DINOLoss(K, 2, 0.04, 0.04, 0, 10).cuda()
+    loss_mod = DINOLoss(K, 2, 0.04, 0.04, 0, 101).cuda()
     center0 = 0.01 * torch.randn(1, K, generator=torch.Generator().manual_seed(5))
     loss_mod.center.copy_(center0)
     so = student(x, metrics, masks, epoch, clusters=None)                                # train.py:232
@@ -110,7 +110,9 @@ def test_step_matches_oracle_gradients():
     assert abs(loss.item() - L.item()) / L.item() <= 1e-3
     assert torch.equal(so["zero"].dense().cpu(), parts["student"]["zero"])
     assert (so["instances_view"].detach().cpu() - parts["student"]["instances_view"].detach()).abs().max() <= 1e-2
-    assert (loss_mod.center.cpu() - parts["center"]).abs().max() <= 1e-4
+    # the centre kernel itself is exact to 1e-5 on identical logits (test_kernels_gpu::test_center_update); here it
+    # averages teacher logits that carry the bf16 operand error (<= 1e-2), scaled by (1 - momentum) = 0.1
+    assert (loss_mod.center.cpu() - parts["center"]).abs().max() <= 3e-4
     low = []
     for n, p in student.named_parameters():
         g = sd[n].grad
