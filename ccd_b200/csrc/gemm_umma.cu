@@ -56,78 +56,64 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
 };
 
+// Normal CDF Phi(x) with the Abramowitz-Stegun 7.1.26 erfc form (|err| <= 1.5e-7 absolute on erf, evaluated as
+// 0.5*erfc(|x|/sqrt2) so the negative tail keeps its relative accuracy): 1 MUFU.RCP + 1 MUFU.EX2 + 7 FMA instead of the
+// ~25-instruction erff.  e_out = exp(-x^2/2) is shared with the derivative.  nn.GELU() is the exact-erf GELU
+// (vision_transformer.py:49-65); gelu(x) = x Phi(x), gelu'(x) = Phi(x) + x exp(-x^2/2)/sqrt(2 pi).
+__device__ __forceinline__ float normal_cdf(float x, float& e_out) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  e_out = e;
+  const float half_erfc = 0.5f * poly * e;
+  return x >= 0.f ? 1.0f - half_erfc : half_erfc;
+}
+__device__ __forceinline__ float gelu_fast(float x) { float e; return x * normal_cdf(x, e); }
+__device__ __forceinline__ float dgelu_fast(float x) { float e; const float c = normal_cdf(x, e); return fmaf(x * 0.3989422804014327f, e, c); }
+
+// Phase 2 of the epilogue: one output row per iteration, lane l owns columns [4l, 4l+4) -> every global access of the
+// warp is one contiguous 512 B (fp32) / 256 B (bf16) row segment.
 template <int EPI>
-__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int col, const float (&acc)[32]) {
-  // 32 consecutive columns of one row; N is a multiple of 8, so validity is decided per group of 8.
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, int row, int col, float4 v) {
   const size_t off = (size_t)row * p.ldc + col;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (col + g * 8 >= p.N) break;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = acc[g * 8 + j];
-    if (p.bias != nullptr) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col + g * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + g * 8 + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  if constexpr (EPI == EPI_BF16) {
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else if constexpr (EPI == EPI_GELU) {
+    const uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = o;
+    // gelu is evaluated on the bf16-rounded pre-activation so that backward (which only has the bf16 copy)
+    // differentiates exactly the function that was applied
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out1) + off) =
+        make_uint2(pack_bf16x2(gelu_fast(bf16lo(o.x)), gelu_fast(bf16hi(o.x))),
+                   pack_bf16x2(gelu_fast(bf16lo(o.y)), gelu_fast(bf16hi(o.y))));
+  } else if constexpr (EPI == EPI_RESID) {
+    const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + off);
+    if (p.seq_scale != nullptr) {
+      const float sc = __ldg(p.seq_scale + (row >> 8));
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
     }
-    if constexpr (EPI == EPI_BF16) {
-      uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                           pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out0) + off + g * 8) = o;
-    } else if constexpr (EPI == EPI_GELU) {
-      uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                           pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out0) + off + g * 8) = o;
-      // gelu is evaluated on the bf16-rounded pre-activation so that backward (which only has the bf16 copy)
-      // differentiates exactly the function that was applied
-      float h[8];
-      h[0] = bf16lo(o.x); h[1] = bf16hi(o.x); h[2] = bf16lo(o.y); h[3] = bf16hi(o.y);
-      h[4] = bf16lo(o.z); h[5] = bf16hi(o.z); h[6] = bf16lo(o.w); h[7] = bf16hi(o.w);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = gelu_erf(h[j]);
-      uint4 o2 = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
-                            pack_bf16x2(h[6], h[7]));
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out1) + off + g * 8) = o2;
-    } else if constexpr (EPI == EPI_RESID) {
-      const float* r = reinterpret_cast<const float*>(p.aux) + off + g * 8;
-      const float4 r0 = *reinterpret_cast<const float4*>(r);
-      const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-      if (p.seq_scale != nullptr) {
-        const float sc = __ldg(p.seq_scale + (row >> 8));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= sc;
-      }
-      float* o = reinterpret_cast<float*>(p.out0) + off + g * 8;
-      *reinterpret_cast<float4*>(o) = make_float4(v[0] + r0.x, v[1] + r0.y, v[2] + r0.z, v[3] + r0.w);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + r1.x, v[5] + r1.y, v[6] + r1.z, v[7] + r1.w);
-    } else if constexpr (EPI == EPI_F32) {
-      float* o = reinterpret_cast<float*>(p.out0) + off + g * 8;
-      if (p.atomic) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
-      } else {
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      }
-    } else if constexpr (EPI == EPI_DGELU) {
-      const uint4 h = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + off + g * 8);
-      v[0] *= dgelu_erf(bf16lo(h.x)); v[1] *= dgelu_erf(bf16hi(h.x));
-      v[2] *= dgelu_erf(bf16lo(h.y)); v[3] *= dgelu_erf(bf16hi(h.y));
-      v[4] *= dgelu_erf(bf16lo(h.z)); v[5] *= dgelu_erf(bf16hi(h.z));
-      v[6] *= dgelu_erf(bf16lo(h.w)); v[7] *= dgelu_erf(bf16hi(h.w));
-      uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                           pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out0) + off + g * 8) = o;
-    } else if constexpr (EPI == EPI_POS) {
-      const float* r = reinterpret_cast<const float*>(p.aux) + (size_t)(row & 255) * p.ldc + col + g * 8;
-      const float4 r0 = __ldg(reinterpret_cast<const float4*>(r));
-      const float4 r1 = __ldg(reinterpret_cast<const float4*>(r + 4));
-      float* o = reinterpret_cast<float*>(p.out0) + off + g * 8;
-      *reinterpret_cast<float4*>(o) = make_float4(v[0] + r0.x, v[1] + r0.y, v[2] + r0.z, v[3] + r0.w);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + r1.x, v[5] + r1.y, v[6] + r1.z, v[7] + r1.w);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + off) = make_float4(v.x + r.x, v.y + r.y, v.z + r.z, v.w + r.w);
+  } else if constexpr (EPI == EPI_F32) {
+    float* o = reinterpret_cast<float*>(p.out0) + off;
+    if (p.atomic) {
+      atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+    } else {
+      *reinterpret_cast<float4*>(o) = v;
     }
+  } else if constexpr (EPI == EPI_DGELU) {
+    const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.aux) + off);
+    v.x *= dgelu_fast(bf16lo(h.x)); v.y *= dgelu_fast(bf16hi(h.x));
+    v.z *= dgelu_fast(bf16lo(h.y)); v.w *= dgelu_fast(bf16hi(h.y));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else if constexpr (EPI == EPI_POS) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (size_t)(row & 255) * p.ldc + col));
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + off) = make_float4(v.x + r.x, v.y + r.y, v.z + r.z, v.w + r.w);
   }
 }
 
@@ -226,20 +212,38 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else {
     // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
+    // Phase 1: TMEM -> registers (thread = row) -> this warp's 32 x BN fp32 staging tile in shared memory (the TMA
+    //          ring is idle once the accumulator is complete), 16-byte chunks XOR-swizzled by the row so that both
+    //          the row-per-thread writes and the row-per-iteration reads hit the minimum number of wavefronts.
+    // Phase 2: one row per iteration, lane l <-> columns [4l,4l+4): coalesced global loads/stores + fused epilogue.
+    static_assert(BN == 128, "epilogue staging assumes 32 sixteen-byte chunks per row");
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+    float* stage = reinterpret_cast<float*>(smem + q * (32 * BN * 4));
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = 0; c < BN / 32; ++c) {
       uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
       tmem_wait_ld();
-      if (row < p.M && n0 + c < p.N) {
-        float acc[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(raw[j]);
-        epilogue_store<EPI>(p, row, n0 + c, acc);
+      for (int j = 0; j < 8; ++j) {
+        const int phys = (c * 8 + j) ^ lane;
+        *reinterpret_cast<uint4*>(stage + lane * BN + phys * 4) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+      }
+    }
+    __syncwarp();
+    const int col = n0 + 4 * lane;
+    if (col < p.N) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const int row_base = m0 + q * 32;
+      const int nrows = min(32, p.M - row_base);
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        float4 v = *reinterpret_cast<const float4*>(stage + r * BN + ((lane ^ r) * 4));
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+        epilogue_row<EPI>(p, row_base + r, col, v);
       }
     }
   }
