@@ -253,6 +253,268 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks a list of work items (m-block, n-block, k-slice).  The per-CTA fixed
+// costs of the one-tile kernel above (launch, barrier init, TMEM alloc, TMA pipeline fill, epilogue drain) dominate
+// when K = 384 gives only 6 k-blocks per tile; here
+//   * the TMA producer streams k-blocks continuously across tile boundaries through a 3-stage ring,
+//   * four 128-column TMEM accumulators decouple the MMA issuer from the epilogue,
+//   * two epilogue warpgroups alternate tiles (TMEM -> regs -> swizzled smem staging -> coalesced global I/O with the
+//     fused epilogue; auxiliary operands are fetched eight rows ahead).
+// 320 threads: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PG_THREADS = 320;
+constexpr int PG_BN = 128;
+constexpr int PG_STAGES = 3;
+constexpr int PG_STAGE_BYTES = (GEMM_BM + PG_BN) * GEMM_BK * 2;   // 32 KB
+constexpr int PG_ACC = 4;                                          // TMEM accumulator buffers (4 x 128 columns)
+constexpr int PG_STAGING = 32 * PG_BN * 4;                         // 16 KB per epilogue warp
+constexpr int PG_SMEM = PG_STAGES * PG_STAGE_BYTES + 8 * PG_STAGING + 256 + 1024;
+
+struct PgWork {
+  int n_tiles_n, n_tiles, n_items;   // items = n_tiles * splits, item -> (z = item / n_tiles, tile = item % n_tiles)
+};
+
+template <int EPI> struct AuxPack { uint32_t a, b, c, d; };
+
+template <int EPI>
+__device__ __forceinline__ AuxPack<EPI> aux_load(const GemmParams& p, int row, int col) {
+  AuxPack<EPI> r{0u, 0u, 0u, 0u};
+  if constexpr (EPI == EPI_RESID) {
+    const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldc + col);
+    r.a = v.x; r.b = v.y; r.c = v.z; r.d = v.w;
+  } else if constexpr (EPI == EPI_DGELU) {
+    const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.aux) + (size_t)row * p.ldc + col);
+    r.a = v.x; r.b = v.y;
+  } else if constexpr (EPI == EPI_POS) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.aux) + (size_t)(row & 255) * p.ldc + col));
+    r.a = v.x; r.b = v.y; r.c = v.z; r.d = v.w;
+  }
+  return r;
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, int col, float4 v, const AuxPack<EPI>& x) {
+  const size_t off = (size_t)row * p.ldc + col;
+  if constexpr (EPI == EPI_RESID) {
+    if (p.seq_scale != nullptr) {
+      const float sc = __ldg(p.seq_scale + (row >> 8));
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    }
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + off) =
+        make_float4(v.x + __uint_as_float(x.a), v.y + __uint_as_float(x.b), v.z + __uint_as_float(x.c), v.w + __uint_as_float(x.d));
+  } else if constexpr (EPI == EPI_DGELU) {
+    v.x *= dgelu_fast(bf16lo(x.a)); v.y *= dgelu_fast(bf16hi(x.a));
+    v.z *= dgelu_fast(bf16lo(x.b)); v.w *= dgelu_fast(bf16hi(x.b));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else if constexpr (EPI == EPI_POS) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + off) =
+        make_float4(v.x + __uint_as_float(x.a), v.y + __uint_as_float(x.b), v.z + __uint_as_float(x.c), v.w + __uint_as_float(x.d));
+  } else {
+    epilogue_row<EPI>(p, row, col, v);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(PG_THREADS, 1)
+gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const GemmParams p_in, const PgWork wk) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + PG_STAGES * PG_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 8 * PG_STAGING);
+  uint64_t* empty_bar = full_bar + PG_STAGES;
+  uint64_t* tmem_full = empty_bar + PG_STAGES;    // [PG_ACC]
+  uint64_t* tmem_empty = tmem_full + PG_ACC;      // [PG_ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + PG_ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kb_total = (p_in.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PG_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < PG_ACC; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: one continuous k-block stream over all items of this CTA =====================
+    if (lane == 0) {
+      uint32_t kbc = 0;   // running k-block counter -> ring slot / phase
+      for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
+        const int z = item / wk.n_tiles, tile = item - z * wk.n_tiles;
+        const int m0 = (tile / wk.n_tiles_n) * GEMM_BM, n0 = (tile % wk.n_tiles_n) * PG_BN;
+        const int kb_begin = z * p_in.kb_per_split;
+        const int nkb = min(kb_total, kb_begin + p_in.kb_per_split) - kb_begin;
+        for (int i = 0; i < nkb; ++i, ++kbc) {
+          const int s = kbc % PG_STAGES;
+          const uint32_t ph = (kbc / PG_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], PG_STAGE_BYTES);
+          uint8_t* sa = smem + s * PG_STAGE_BYTES;
+          uint8_t* sb = sa + GEMM_BM * GEMM_BK * 2;
+          const int k0 = (kb_begin + i) * GEMM_BK;
+          if (!p_in.a_mn) {
+            tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
+            tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
+          }
+          if (!p_in.b_mn) {
+            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+          } else {
+            tma_load_2d(sb, &tmB, &full_bar[s], n0, k0);
+            tma_load_2d(sb + 8192, &tmB, &full_bar[s], n0 + 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, PG_BN, p_in.a_mn, p_in.b_mn);
+      uint32_t kbc = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x, ++it) {
+        const int z = item / wk.n_tiles;
+        const int kb_begin = z * p_in.kb_per_split;
+        const int nkb = min(kb_total, kb_begin + p_in.kb_per_split) - kb_begin;
+        const int acc = it % PG_ACC;
+        mbar_wait(&tmem_empty[acc], ((it / PG_ACC) & 1) ^ 1);     // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * PG_BN;
+        for (int i = 0; i < nkb; ++i, ++kbc) {
+          const int s = kbc % PG_STAGES;
+          const uint32_t ph = (kbc / PG_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * PG_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + GEMM_BM * GEMM_BK * 2;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = p_in.a_mn ? umma_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                          : umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = p_in.b_mn ? umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                          : umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_ss(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: group g takes items it = g, g+2, ... of this CTA =====================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    float* stage = reinterpret_cast<float*>(staging + (warp - 2) * PG_STAGING);
+    int it = 0;
+    for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x, ++it) {
+      if ((it & 1) != g) continue;
+      GemmParams p = p_in;
+      const int z = item / wk.n_tiles, tile = item - z * wk.n_tiles;
+      if (z != 0) p.bias = nullptr;
+      const int m0 = (tile / wk.n_tiles_n) * GEMM_BM, n0 = (tile % wk.n_tiles_n) * PG_BN;
+      const int acc = it % PG_ACC;
+      const int col = n0 + 4 * lane;
+      const int row_base = m0 + q * 32;
+      const int nrows = max(0, min(32, p.M - row_base));
+      const bool col_ok = col < p.N;
+      // first batch of auxiliary rows is requested before the accumulator is waited for
+      AuxPack<EPI> ax[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (col_ok && j < nrows) ax[j] = aux_load<EPI>(p, row_base + j, col);
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+
+      mbar_wait(&tmem_full[acc], (it / PG_ACC) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < PG_BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * PG_BN + c * 32), raw);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int phys = (c * 8 + j) ^ lane;
+          *reinterpret_cast<uint4*>(stage + lane * PG_BN + phys * 4) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);            // accumulator drained: the MMA issuer may overwrite it
+      __syncwarp();
+      if (col_ok) {
+#pragma unroll 1
+        for (int r0 = 0; r0 < nrows; r0 += 8) {
+          AuxPack<EPI> nx[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (r0 + 8 + j < nrows) nx[j] = aux_load<EPI>(p, row_base + r0 + 8 + j, col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = r0 + j;
+            if (r < nrows) {
+              float4 v = *reinterpret_cast<const float4*>(stage + r * PG_BN + ((lane ^ r) * 4));
+              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+              epilogue_row_aux<EPI>(p, row_base + r, col, v, ax[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ax[j] = nx[j];
+        }
+      }
+      __syncwarp();                              // staging tile is rewritten by the next item of this warp
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int g_gemm_variant = 1;   // 1 = persistent (default), 0 = one tile per CTA
+
+template <int EPI>
+static int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits,
+                                  cudaStream_t stream) {
+  static bool attr_set = false;
+  static int num_sms = 148;
+  if (!attr_set) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+    int dev = 0;
+    CCD_CUDA_CHECK(cudaGetDevice(&dev));
+    CCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  PgWork wk;
+  wk.n_tiles_n = (p.N + PG_BN - 1) / PG_BN;
+  wk.n_tiles = wk.n_tiles_n * ((p.M + GEMM_BM - 1) / GEMM_BM);
+  wk.n_items = wk.n_tiles * splits;
+  const int grid = wk.n_items < num_sms ? wk.n_items : num_sms;
+  gemm_umma_persistent_kernel<EPI><<<grid, PG_THREADS, PG_SMEM, stream>>>(tmA, tmB, p, wk);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
 template <int EPI, int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits,
                        cudaStream_t stream) {
@@ -304,6 +566,16 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
   p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0; p.kb_per_split = kb_per;
   p.bias = bias; p.out0 = out0; p.out1 = out1; p.aux = aux; p.ldc = ldc; p.atomic = (splits > 1) ? 1 : 0;
   p.seq_scale = seq_scale;
+  if (g_gemm_variant == 1) {
+    switch (epi) {
+      case EPI_BF16:  return launch_gemm_persistent<EPI_BF16>(tmA, tmB, p, splits, stream);
+      case EPI_GELU:  return launch_gemm_persistent<EPI_GELU>(tmA, tmB, p, splits, stream);
+      case EPI_RESID: return launch_gemm_persistent<EPI_RESID>(tmA, tmB, p, splits, stream);
+      case EPI_F32:   return launch_gemm_persistent<EPI_F32>(tmA, tmB, p, splits, stream);
+      case EPI_DGELU: return launch_gemm_persistent<EPI_DGELU>(tmA, tmB, p, splits, stream);
+      case EPI_POS:   return launch_gemm_persistent<EPI_POS>(tmA, tmB, p, splits, stream);
+    }
+  }
   switch (epi) {
     case EPI_BF16:  return launch_gemm<EPI_BF16, BN>(tmA, tmB, p, splits, stream);
     case EPI_GELU:  return launch_gemm<EPI_GELU, BN>(tmA, tmB, p, splits, stream);
@@ -312,5 +584,11 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
     case EPI_DGELU: return launch_gemm<EPI_DGELU, BN>(tmA, tmB, p, splits, stream);
     case EPI_POS:   return launch_gemm<EPI_POS, BN>(tmA, tmB, p, splits, stream);
   }
+  return CCD_ERR_ARG;
+}
+
+// debug / A-B switch: key 0 = GEMM variant (1 persistent, 0 one-tile-per-CTA)
+extern "C" int ccd_set_option(int key, int value) {
+  if (key == 0) { g_gemm_variant = value ? 1 : 0; return CCD_OK; }
   return CCD_ERR_ARG;
 }

@@ -229,6 +229,204 @@ static int launch_mhsa_fwd(const CUtensorMap& tm, const MhsaFwdParams& p, int S,
   return CCD_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant (variant 2): one CTA per SM loops over (sequence, head) work items; both 128-query tiles of an
+// item share ONE K/V load; Q/K/V shared-memory buffers are double buffered (TMA prefetch of item i+1 under item i),
+// two softmax warpgroups (one per query tile) ping-pong on the MUFU while the single MMA thread alternates
+// S_t = Q_t K^T and O_t = P_t V.  TMEM: S0 [0,256) S1 [256,512); P_t aliases the first 128 columns of S_t, O_t the
+// next 64.  320 threads: warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 softmax tile 0, warps 6-9 softmax tile 1.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ATT2_THREADS = 320;
+constexpr int ATT2_BUF = 3 * ATT_N * ATT_D * 2;        // Q + K + V = 96 KB
+constexpr int ATT2_SMEM = 2 * ATT2_BUF + 256 + 1024;
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const MhsaFwdParams p, int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATT2_BUF);
+  uint64_t* full_qk = bars;        // [2]
+  uint64_t* full_v = bars + 2;     // [2]
+  uint64_t* empty = bars + 4;      // [2]
+  uint64_t* s_full = bars + 6;     // [2] per query tile
+  uint64_t* p_full = bars + 8;     // [2]
+  uint64_t* o_full = bars + 10;    // [2]
+  uint64_t* tmem_free = bars + 12; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_qk[i], 1);
+      mbar_init(&full_v[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&tmem_free[i], 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQKV);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t kph = (it >> 1) & 1;
+        const int s = w / p.H, h = w - s * p.H;
+        const int row0 = s * ATT_N;
+        uint8_t* buf = smem + b * ATT2_BUF;
+        mbar_wait(&empty[b], kph ^ 1);
+        mbar_arrive_expect_tx(&full_qk[b], 2 * ATT_N * ATT_D * 2);
+        tma_load_2d(buf, &tmQKV, &full_qk[b], h * ATT_D, row0);
+        tma_load_2d(buf + 16384, &tmQKV, &full_qk[b], h * ATT_D, row0 + 128);
+        tma_load_2d(buf + 32768, &tmQKV, &full_qk[b], p.E + h * ATT_D, row0);
+        tma_load_2d(buf + 49152, &tmQKV, &full_qk[b], p.E + h * ATT_D, row0 + 128);
+        mbar_arrive_expect_tx(&full_v[b], ATT_N * ATT_D * 2);
+        tma_load_2d(buf + 65536, &tmQKV, &full_v[b], 2 * p.E + h * ATT_D, row0);
+        tma_load_2d(buf + 81920, &tmQKV, &full_v[b], 2 * p.E + h * ATT_D, row0 + 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t kph = (it >> 1) & 1, ph = it & 1;
+        const uint32_t buf = smem_u32(smem + b * ATT2_BUF);
+        mbar_wait(&full_qk[b], kph);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&tmem_free[t], ph ^ 1);       // previous item's O_t has been read out of TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k)
+            umma_ss(tmem_base + t * 256, umma_smem_desc_sw128(buf + t * 16384 + k * 32, 16, 1024),
+                    umma_smem_desc_sw128(buf + 32768 + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[t]);
+        }
+        mbar_wait(&full_v[b], kph);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < ATT_N / 16; ++k)
+            umma_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8,
+                    umma_smem_desc_sw128(buf + 65536 + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+          umma_commit(&o_full[t]);
+        }
+        umma_commit(&empty[b]);                   // Q/K/V buffer reusable once every MMA of this item retired
+      }
+    }
+    __syncwarp();
+  } else {
+    const int t = (warp - 2) >> 2;                // query tile / softmax warpgroup
+    const int q = warp & 3;                       // TMEM lane quarter
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem_base + t * 256, tO = tS + 128;
+    const float c = p.scale_log2;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int s = w / p.H, h = w - s * p.H;
+      mbar_wait(&s_full[t], ph);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < ATT_N / 32; ++ch) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tS + lane_sel + ch * 32, raw);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+      }
+      const float mc = mx * c;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < ATT_N / 32; ++ch) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tS + lane_sel + ch * 32, raw);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * j]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * j + 1]), c, -mc));
+          pk[j] = pack_bf16x2(p0, p1);
+          sum += bf16lo(pk[j]) + bf16hi(pk[j]);
+        }
+        tmem_st_32x16(tS + lane_sel + ch * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+
+      mbar_wait(&o_full[t], ph);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      const size_t tok = (size_t)s * ATT_N + t * ATT_BM + r;
+      bf16* orow = p.out + tok * p.E + h * ATT_D;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tO + lane_sel + half * 32, raw);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(raw[8 * g + 0]) * inv, __uint_as_float(raw[8 * g + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(raw[8 * g + 2]) * inv, __uint_as_float(raw[8 * g + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(raw[8 * g + 4]) * inv, __uint_as_float(raw[8 * g + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(raw[8 * g + 6]) * inv, __uint_as_float(raw[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + half * 32 + g * 8) = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_free[t]);
+      if (p.lse2 != nullptr) p.lse2[((size_t)s * p.H + h) * ATT_N + t * ATT_BM + r] = mc + log2f(sum);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int launch_mhsa_fwd_persistent(const CUtensorMap& tm, const MhsaFwdParams& p, int S, cudaStream_t stream) {
+  static bool attr_set = false;
+  static int num_sms = 148;
+  if (!attr_set) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(mhsa_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+    int dev = 0;
+    CCD_CUDA_CHECK(cudaGetDevice(&dev));
+    CCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int n_items = S * p.H;
+  const int grid = n_items < num_sms ? n_items : num_sms;
+  mhsa_fwd_persistent_kernel<<<grid, ATT2_THREADS, ATT2_SMEM, stream>>>(tm, p, n_items);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
 }  // namespace ccd
 
 using namespace ccd;
@@ -247,5 +445,6 @@ extern "C" int ccd_mhsa_fwd(const void* qkv, void* out, float* lse2, int S, int 
   p.H = H;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   if (variant == 1) return launch_mhsa_fwd<false>(tm, p, S, stream);
+  if (variant == 2) return launch_mhsa_fwd_persistent(tm, p, S, stream);
   return launch_mhsa_fwd<true>(tm, p, S, stream);
 }

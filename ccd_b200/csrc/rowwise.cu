@@ -84,12 +84,28 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
   for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * E);
-    float4 v[LN_MAX_V4], g[LN_MAX_V4];
+    float4 v[LN_MAX_V4], d[LN_MAX_V4], rs[LN_MAX_V4], g[LN_MAX_V4];
+    // issue every global load of the row up front (x, dy, residual gradient): the reductions below then overlap
+    // with the loads of the other warps instead of serialising three DRAM round trips per row
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        v[i] = xr[c];
+        if constexpr (DY_BF16) {
+          const uint2 pk = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (size_t)row * E)[c];
+          d[i] = make_float4(bf16lo(pk.x), bf16hi(pk.x), bf16lo(pk.y), bf16hi(pk.y));
+        } else {
+          d[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * E)[c];
+        }
+        rs[i] = resid ? reinterpret_cast<const float4*>(resid + (size_t)row * E)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAX_V4; ++i) {
       const int c = lane + i * 32;
-      if (c < nv) { v[i] = xr[c]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+      if (c < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
     const float mean = warp_sum(s) / (float)E;
     float q = 0.f;
@@ -107,18 +123,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     for (int i = 0; i < LN_MAX_V4; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
-        float4 d;
-        if constexpr (DY_BF16) {
-          const uint2 pk = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (size_t)row * E)[c];
-          d = make_float4(bf16lo(pk.x), bf16hi(pk.x), bf16lo(pk.y), bf16hi(pk.y));
-        } else {
-          d = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * E)[c];
-        }
         v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
-        adg[i].x += d.x * v[i].x; adg[i].y += d.y * v[i].y; adg[i].z += d.z * v[i].z; adg[i].w += d.w * v[i].w;
-        adb[i].x += d.x; adb[i].y += d.y; adb[i].z += d.z; adb[i].w += d.w;
+        adg[i].x += d[i].x * v[i].x; adg[i].y += d[i].y * v[i].y; adg[i].z += d[i].z * v[i].z; adg[i].w += d[i].w * v[i].w;
+        adb[i].x += d[i].x; adb[i].y += d[i].y; adb[i].z += d[i].z; adb[i].w += d[i].w;
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        g[i] = make_float4(d[i].x * gm.x, d[i].y * gm.y, d[i].z * gm.z, d[i].w * gm.w);
         m1 += g[i].x + g[i].y + g[i].z + g[i].w;
         m2 += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
       }
@@ -130,14 +139,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       const int c = lane + i * 32;
       if (c < nv) {
         float4 o;
-        o.x = rstd * (g[i].x - m1 - v[i].x * m2);
-        o.y = rstd * (g[i].y - m1 - v[i].y * m2);
-        o.z = rstd * (g[i].z - m1 - v[i].z * m2);
-        o.w = rstd * (g[i].w - m1 - v[i].w * m2);
-        if (resid) {
-          const float4 r = reinterpret_cast<const float4*>(resid + (size_t)row * E)[c];
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        o.x = rstd * (g[i].x - m1 - v[i].x * m2) + rs[i].x;
+        o.y = rstd * (g[i].y - m1 - v[i].y * m2) + rs[i].y;
+        o.z = rstd * (g[i].z - m1 - v[i].z * m2) + rs[i].z;
+        o.w = rstd * (g[i].w - m1 - v[i].w * m2) + rs[i].w;
         if (dx_f32) reinterpret_cast<float4*>(dx_f32 + (size_t)row * E)[c] = o;
         if (dx_bf16) {
           // the bf16 copy feeds the NEXT residual branch's grads; DropPath scales that branch per sequence

@@ -43,6 +43,9 @@ def _bind():
         fn.argtypes = types
         fn.restype = ctypes.c_int
         _FN[name] = fn
+    import os
+    if "CCD_GEMM_VARIANT" in os.environ:            # debug A/B switch (1 = persistent [default], 0 = one tile per CTA)
+        _FN["ccd_set_option"](0, int(os.environ["CCD_GEMM_VARIANT"]))
 
 
 def _call(name, *args, work=None):
@@ -115,7 +118,12 @@ def linear_wgrad(dy_bf16, x_bf16, dw_f32_zeroed):
     return gemm(dy_bf16, x_bf16, N, K, T, 1, 1, EPI_F32, None, dw_f32_zeroed, None, None, dw_f32_zeroed.shape[1], sp)
 
 
-def mhsa_fwd(qkv, S, H, want_lse=True, variant=0):
+MHSA_FWD_VARIANT = int(__import__("os").environ.get("CCD_MHSA_FWD_VARIANT", "0"))
+
+
+def mhsa_fwd(qkv, S, H, want_lse=True, variant=None):
+    if variant is None:
+        variant = MHSA_FWD_VARIANT
     E = H * 64
     out = torch.empty(S * 256, E, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(S, H, 256, dtype=torch.float32, device=qkv.device) if want_lse else None

@@ -105,6 +105,9 @@ int ccd_char_pool_fwd(const void* tokens, int tokens_bf16, const void* bits, con
 int ccd_char_pool_bwd(const float* drows, const void* bits, const int* tot4, const int* cnt, const int* offs, float* dtokens,
                       int n_view, int E, void* stream);
 
+/* debug / A-B switches (process-global): key 0 = GEMM variant (1 = persistent [default], 0 = one tile per CTA) */
+int ccd_set_option(int key, int value);
+
 /* library identification (build sanity) */
 int ccd_abi_version(void);
 

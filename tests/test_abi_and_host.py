@@ -11,7 +11,7 @@ def test_library_exports_every_declared_symbol():
     from ccd_b200 import lib
     L = lib.load()
     syms = lib.declared_symbols()
-    assert len(syms) >= 28
+    assert len(syms) >= 29
     for s in syms:
         assert hasattr(L, s), s
     assert L.ccd_abi_version() == 1
@@ -21,6 +21,7 @@ def test_argument_validation_without_gpu():
     from ccd_b200 import ops
     ops._bind()
     f = ops._FN
+    assert f["ccd_set_option"](99, 0) == -1 and f["ccd_set_option"](0, 1) == 0
     assert f["ccd_gemm_bf16"](None, None, 128, 128, 64, 0, 0, 0, None, None, None, None, None, 0, 1, None) == -1
     assert f["ccd_gemm_bf16"](1, 1, 128, 100, 64, 0, 0, 0, None, 1, None, None, None, 0, 1, None) == -1     # N % 8
     assert f["ccd_mhsa_fwd"](None, None, None, 1, 3, 0, None) == -1

@@ -116,8 +116,8 @@ def _attn_ref(qkv, S, H):
     return o, lse2, p
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("S,H", [(2, 3), (5, 6)])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("S,H", [(2, 3), (5, 6), (70, 6)])
 def test_mhsa_fwd(ops, variant, S, H):
     g = torch.Generator(device="cuda").manual_seed(S * 10 + H)
     qkv = _bf(torch.randn(S * 256, 3 * H * 64, device="cuda", generator=g) * 1.5)
