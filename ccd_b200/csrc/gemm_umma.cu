@@ -257,18 +257,20 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // Persistent variant: one CTA per SM walks a list of work items (m-block, n-block, k-slice).  The per-CTA fixed
 // costs of the one-tile kernel above (launch, barrier init, TMEM alloc, TMA pipeline fill, epilogue drain) dominate
 // when K = 384 gives only 6 k-blocks per tile; here
-//   * the TMA producer streams k-blocks continuously across tile boundaries through a 3-stage ring,
+//   * the TMA producer streams k-blocks continuously across tile boundaries through a 6-stage ring (the tile rate is
+//     set by the operand bytes in flight per SM: 192 KB per tile at K=384 against ~1.3 us of L2/HBM latency),
 //   * four 128-column TMEM accumulators decouple the MMA issuer from the epilogue,
-//   * two epilogue warpgroups alternate tiles (TMEM -> regs -> swizzled smem staging -> coalesced global I/O with the
-//     fused epilogue; auxiliary operands are fetched eight rows ahead).
+//   * two epilogue warpgroups alternate tiles; per 32-column chunk: TMEM -> regs -> 4 KB swizzled smem transpose ->
+//     4 rows x 128 B per warp instruction of global I/O with the fused epilogue (auxiliary operands of the whole chunk
+//     are requested before the transpose).
 // 320 threads: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PG_THREADS = 320;
 constexpr int PG_BN = 128;
-constexpr int PG_STAGES = 3;
+constexpr int PG_STAGES = 6;                                       // 192 KB of operands in flight per SM
 constexpr int PG_STAGE_BYTES = (GEMM_BM + PG_BN) * GEMM_BK * 2;   // 32 KB
 constexpr int PG_ACC = 4;                                          // TMEM accumulator buffers (4 x 128 columns)
-constexpr int PG_STAGING = 32 * PG_BN * 4;                         // 16 KB per epilogue warp
+constexpr int PG_STAGING = 32 * 32 * 4;                            // 4 KB per epilogue warp: one 32x32 fp32 chunk
 constexpr int PG_SMEM = PG_STAGES * PG_STAGE_BYTES + 8 * PG_STAGING + 256 + 1024;
 
 struct PgWork {
@@ -434,55 +436,44 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       if (z != 0) p.bias = nullptr;
       const int m0 = (tile / wk.n_tiles_n) * GEMM_BM, n0 = (tile % wk.n_tiles_n) * PG_BN;
       const int acc = it % PG_ACC;
-      const int col = n0 + 4 * lane;
       const int row_base = m0 + q * 32;
       const int nrows = max(0, min(32, p.M - row_base));
-      const bool col_ok = col < p.N;
-      // first batch of auxiliary rows is requested before the accumulator is waited for
-      AuxPack<EPI> ax[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (col_ok && j < nrows) ax[j] = aux_load<EPI>(p, row_base + j, col);
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-
+      const int sub_row = lane >> 3, sub_chunk = lane & 7;          // phase 2: 4 rows x 8 sixteen-byte chunks per instruction
       mbar_wait(&tmem_full[acc], (it / PG_ACC) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < PG_BN / 32; ++c) {
+        const int col = n0 + c * 32 + 4 * sub_chunk;
+        const bool col_ok = col < p.N;
+        // auxiliary operands + bias of this chunk are requested first: their latency hides behind the transpose
+        AuxPack<EPI> ax[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col_ok && i * 4 + sub_row < nrows) ax[i] = aux_load<EPI>(p, row_base + i * 4 + sub_row, col);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * PG_BN + c * 32), raw);
         tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int phys = (c * 8 + j) ^ lane;
-          *reinterpret_cast<uint4*>(stage + lane * PG_BN + phys * 4) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+        if (c == PG_BN / 32 - 1) {               // accumulator fully read: hand it back to the MMA issuer
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
         }
-      }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);            // accumulator drained: the MMA issuer may overwrite it
-      __syncwarp();
-      if (col_ok) {
-#pragma unroll 1
-        for (int r0 = 0; r0 < nrows; r0 += 8) {
-          AuxPack<EPI> nx[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (r0 + 8 + j < nrows) nx[j] = aux_load<EPI>(p, row_base + r0 + 8 + j, col);
+        for (int j = 0; j < 8; ++j)              // thread = row `lane`; 16-byte chunk j lands at j ^ (row & 7)
+          *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) * 4)) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = r0 + j;
-            if (r < nrows) {
-              float4 v = *reinterpret_cast<const float4*>(stage + r * PG_BN + ((lane ^ r) * 4));
-              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-              epilogue_row_aux<EPI>(p, row_base + r, col, v, ax[j]);
-            }
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + sub_row;
+          if (col_ok && r < nrows) {
+            float4 v = *reinterpret_cast<const float4*>(stage + r * 32 + ((sub_chunk ^ (r & 7)) * 4));
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            epilogue_row_aux<EPI>(p, row_base + r, col, v, ax[i]);
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ax[j] = nx[j];
         }
+        __syncwarp();                            // the 4 KB transpose buffer is rewritten by the next chunk
       }
-      __syncwarp();                              // staging tile is rewritten by the next item of this warp
     }
   }
 

@@ -99,31 +99,45 @@ def test_step_matches_reference_golden(name):
 
 
 def test_step_matches_oracle_gradients():
-    """cfg1 (ViT-Tiny, B=4, out_dim 65536) against the fp32 oracle on the host: every gradient tensor by cosine."""
+    """cfg1 (ViT-Tiny, B=4, out_dim 65536) against the fp32 oracle: every gradient tensor by cosine.
+
+    BASELINE.md quotes cosine >= 0.999; with bf16 tensor-core operands that bar is met by the head and the deeper blocks,
+    but NOT by the earliest layers / the seg branch on this sharpened (T=0.04, 65536-way) loss -- neither by this path
+    nor by stock PyTorch bf16 autocast (tests/grad_parity_report.py: e.g. pos_embed 0.9917 here vs 0.9902 stock).  The
+    bar asserted here is therefore: every tensor >= 0.98 AND no worse than what stock autocast-bf16 PyTorch gets on
+    the same step (oracle restatement under torch.autocast on the GPU) by more than 3e-3, AND >= 0.999 for the head."""
     import ccd_oracle as O
     arch, E, B, K, sseed, tseed, std, norm_last = CASES["cfg1_tiny_b4"]
     student, teacher, ssd, tsd = build(arch, E, K, sseed, tseed, std, norm_last)
     loss, loss_mod, so, to, _, (x, masks, metrics, center0) = run_step(student, teacher, K, B)
-    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in ssd.items()}
-    L, parts = O.pretrain_loss(sd, tsd, arch, x.cpu(), metrics.cpu(), masks.cpu(), center0, 0, 0.04)
-    L.backward()
+
+    def oracle(device, autocast):
+        sd = {k: v.clone().to(device).requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in ssd.items()}
+        td = {k: v.to(device) for k, v in tsd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            L, parts = O.pretrain_loss(sd, td, arch, x.to(device), metrics.to(device), masks.to(device), center0.to(device), 0, 0.04)
+        L.backward()
+        return L, parts, {k: v.grad.detach().float().cpu() for k, v in sd.items() if v.grad is not None}
+
+    L, parts, g32 = oracle("cpu", False)
+    _, _, gbf = oracle("cuda", True)
     assert abs(loss.item() - L.item()) / L.item() <= 1e-3
     assert torch.equal(so["zero"].dense().cpu(), parts["student"]["zero"])
     assert (so["instances_view"].detach().cpu() - parts["student"]["instances_view"].detach()).abs().max() <= 1e-2
     # the centre kernel itself is exact to 1e-5 on identical logits (test_kernels_gpu::test_center_update); here it
     # averages teacher logits that carry the bf16 operand error (<= 1e-2), scaled by (1 - momentum) = 0.1
     assert (loss_mod.center.cpu() - parts["center"]).abs().max() <= 3e-4
-    low = []
+    bad = []
     for n, p in student.named_parameters():
-        g = sd[n].grad
+        g = g32.get(n)
         if g is None or g.norm() < 1e-7:
             continue
         assert p.grad is not None, n
-        c = cosine(p.grad.cpu(), g)
-        if c < 0.999:
-            low.append((n, round(c, 5), g.norm().item()))
-    assert all(c >= 0.98 for _, c, _ in low), low
-    assert len(low) <= 12, low
+        c, c_stock = cosine(p.grad.cpu(), g), cosine(gbf[n], g)
+        floor = 0.999 if n.startswith("head.") else 0.98
+        if c < floor or c < c_stock - 3e-3:
+            bad.append((n, round(c, 5), round(c_stock, 5)))
+    assert not bad, bad
 
 
 def test_teacher_accepts_dense_clusters_and_ema():
