@@ -265,13 +265,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //     are requested before the transpose).
 // 320 threads: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int PG_THREADS = 320;
 constexpr int PG_BN = 128;
-constexpr int PG_STAGES = 6;                                       // 192 KB of operands in flight per SM
 constexpr int PG_STAGE_BYTES = (GEMM_BM + PG_BN) * GEMM_BK * 2;   // 32 KB
 constexpr int PG_ACC = 4;                                          // TMEM accumulator buffers (4 x 128 columns)
 constexpr int PG_STAGING = 32 * 32 * 4;                            // 4 KB per epilogue warp: one 32x32 fp32 chunk
-constexpr int PG_SMEM = PG_STAGES * PG_STAGE_BYTES + 8 * PG_STAGING + 256 + 1024;
+// NG epilogue warpgroups: 2 for the light epilogues (6-stage ring = 192 KB of operands in flight per SM), 4 for the
+// GELU / GELU' epilogues, which are instruction-issue bound (~20 instructions per output element) with fewer warps.
+template <int NG> struct PgCfg {
+  static constexpr int STAGES = (NG == 2) ? 6 : 5;
+  static constexpr int THREADS = 64 + NG * 128;
+  static constexpr int SMEM = STAGES * PG_STAGE_BYTES + NG * 4 * PG_STAGING + 256 + 1024;
+};
 
 struct PgWork {
   int n_tiles_n, n_tiles, n_items;   // items = n_tiles * splits, item -> (z = item / n_tiles, tile = item % n_tiles)
@@ -317,14 +321,15 @@ __device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, i
   }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(PG_THREADS, 1)
+template <int EPI, int NG>
+__global__ void __launch_bounds__(PgCfg<NG>::THREADS, 1)
 gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const GemmParams p_in, const PgWork wk) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int PG_STAGES = PgCfg<NG>::STAGES;
   uint8_t* staging = smem + PG_STAGES * PG_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 8 * PG_STAGING);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + NG * 4 * PG_STAGING);
   uint64_t* empty_bar = full_bar + PG_STAGES;
   uint64_t* tmem_full = empty_bar + PG_STAGES;    // [PG_ACC]
   uint64_t* tmem_empty = tmem_full + PG_ACC;      // [PG_ACC]
@@ -424,13 +429,13 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: group g takes items it = g, g+2, ... of this CTA =====================
+    // ===================== epilogue: group g takes items it = g, g+NG, ... of this CTA =====================
     const int g = (warp - 2) >> 2;
     const int q = warp & 3;
     float* stage = reinterpret_cast<float*>(staging + (warp - 2) * PG_STAGING);
     int it = 0;
     for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x, ++it) {
-      if ((it & 1) != g) continue;
+      if ((it % NG) != g) continue;
       GemmParams p = p_in;
       const int z = item / wk.n_tiles, tile = item - z * wk.n_tiles;
       if (z != 0) p.bias = nullptr;
@@ -484,13 +489,14 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 
 static int g_gemm_variant = 1;   // 1 = persistent (default), 0 = one tile per CTA
 
-template <int EPI>
+template <int EPI, int NG>
 static int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits,
                                   cudaStream_t stream) {
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
-    CCD_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<EPI, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        PgCfg<NG>::SMEM));
     int dev = 0;
     CCD_CUDA_CHECK(cudaGetDevice(&dev));
     CCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -501,7 +507,7 @@ static int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB
   wk.n_tiles = wk.n_tiles_n * ((p.M + GEMM_BM - 1) / GEMM_BM);
   wk.n_items = wk.n_tiles * splits;
   const int grid = wk.n_items < num_sms ? wk.n_items : num_sms;
-  gemm_umma_persistent_kernel<EPI><<<grid, PG_THREADS, PG_SMEM, stream>>>(tmA, tmB, p, wk);
+  gemm_umma_persistent_kernel<EPI, NG><<<grid, PgCfg<NG>::THREADS, PgCfg<NG>::SMEM, stream>>>(tmA, tmB, p, wk);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }
@@ -559,12 +565,12 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
   p.seq_scale = seq_scale;
   if (g_gemm_variant == 1) {
     switch (epi) {
-      case EPI_BF16:  return launch_gemm_persistent<EPI_BF16>(tmA, tmB, p, splits, stream);
-      case EPI_GELU:  return launch_gemm_persistent<EPI_GELU>(tmA, tmB, p, splits, stream);
-      case EPI_RESID: return launch_gemm_persistent<EPI_RESID>(tmA, tmB, p, splits, stream);
-      case EPI_F32:   return launch_gemm_persistent<EPI_F32>(tmA, tmB, p, splits, stream);
-      case EPI_DGELU: return launch_gemm_persistent<EPI_DGELU>(tmA, tmB, p, splits, stream);
-      case EPI_POS:   return launch_gemm_persistent<EPI_POS>(tmA, tmB, p, splits, stream);
+      case EPI_BF16:  return launch_gemm_persistent<EPI_BF16, 2>(tmA, tmB, p, splits, stream);
+      case EPI_GELU:  return launch_gemm_persistent<EPI_GELU, 4>(tmA, tmB, p, splits, stream);
+      case EPI_RESID: return launch_gemm_persistent<EPI_RESID, 2>(tmA, tmB, p, splits, stream);
+      case EPI_F32:   return launch_gemm_persistent<EPI_F32, 2>(tmA, tmB, p, splits, stream);
+      case EPI_DGELU: return launch_gemm_persistent<EPI_DGELU, 4>(tmA, tmB, p, splits, stream);
+      case EPI_POS:   return launch_gemm_persistent<EPI_POS, 2>(tmA, tmB, p, splits, stream);
     }
   }
   switch (epi) {

@@ -20,7 +20,7 @@ namespace ccd {
 
 constexpr int ATB_N = 256;
 constexpr int ATB_D = 64;
-constexpr int ATB_THREADS = 192;
+constexpr int ATB_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 = two softmax-gradient warpgroups
 
 struct MhsaBwdParams {
   const bf16* o;      // [T, E] forward output
@@ -102,7 +102,7 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(bar_qk, 1);
     mbar_init(bar_vdo, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_pd, 128);
+    mbar_init(bar_pd, 256);
     mbar_init(bar_acc, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
@@ -175,11 +175,15 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
     __syncwarp();
   } else {
+    // Two warpgroups share the 128 key rows (TMEM lanes) and split the 128 query columns of each pair in halves;
+    // the epilogues are split the same way (dK | dV, dQ_0 | dQ_1).
+    const int wg = (warp - 2) >> 2;
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;  // key row within tile j / query row in the epilogues
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    // delta[q] = sum_d O[q,d] dO[q,d]; lse2 -> smem
-    for (int rr = r; rr < ATB_N; rr += 128) {
+    // delta[q] = sum_d O[q,d] dO[q,d]; lse2 -> smem   (256 threads <-> 256 query rows)
+    {
+      const int rr = wg * 128 + r;
       const bf16* po = p.o + ((size_t)row0 + rr) * p.E + h * ATB_D;
       const bf16* pd = p.d_o + ((size_t)row0 + rr) * p.E + h * ATB_D;
       float acc = 0.f;
@@ -189,7 +193,7 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       sDelta[rr] = acc;
       sLse[rr] = p.lse2[((size_t)s * p.H + h) * ATB_N + rr];
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const float c = p.scale_log2;
 
     for (int t = 0; t < 4; ++t) {
@@ -198,7 +202,8 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (t > 0) mbar_wait(bar_acc, (t - 1) & 1);   // previous pair's MMAs no longer read P^T / dS^T smem
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {  // 32 queries per chunk
+      for (int cc = 0; cc < 2; ++cc) {  // this warpgroup's two 32-query chunks
+        const int ch = wg * 2 + cc;
         uint32_t rs[32], rd[32];
         tmem_ld_32x32(tST + lane_sel + ch * 32, rs);
         tmem_ld_32x32(tDPT + lane_sel + ch * 32, rd);
@@ -227,20 +232,19 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();
       mbar_arrive(bar_pd);
       if (i == 1) {
-        // key tile j finished: dK_j, dV_j -> dqkv
+        // key tile j finished: dK_j (warpgroup 0) and dV_j (warpgroup 1) -> dqkv
         mbar_wait(bar_acc, t & 1);
         tc_fence_after();
         bf16* drow = p.dqkv + ((size_t)row0 + j * 128 + r) * (3 * p.E) + h * ATB_D;
-        store_tmem_row64(tDK + lane_sel, drow + p.E);
-        store_tmem_row64(tDV + lane_sel, drow + 2 * p.E);
+        if (wg == 0) store_tmem_row64(tDK + lane_sel, drow + p.E);
+        else         store_tmem_row64(tDV + lane_sel, drow + 2 * p.E);
         tc_fence_before();
       }
     }
-    // dQ tiles (bar_acc of the last pair has been waited on above)
-#pragma unroll 1
-    for (int i = 0; i < 2; ++i) {
-      bf16* drow = p.dqkv + ((size_t)row0 + i * 128 + r) * (3 * p.E) + h * ATB_D;
-      store_tmem_row64(tDQ + i * 64 + lane_sel, drow);
+    // dQ tiles (bar_acc of the last pair has been waited on above): warpgroup w stores dQ_w
+    {
+      bf16* drow = p.dqkv + ((size_t)row0 + wg * 128 + r) * (3 * p.E) + h * ATB_D;
+      store_tmem_row64(tDQ + wg * 64 + lane_sel, drow);
     }
   }
 

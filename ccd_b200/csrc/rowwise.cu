@@ -69,18 +69,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const void* __restrict__ dy_, const float* __restrict__ resid,
                                                             float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            const float* __restrict__ bf16_seq_scale, int rows, int E,
-                                                            float eps) {
-  __shared__ float s_dg[512], s_db[512];
-  for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+                                                            const float* __restrict__ bf16_seq_scale,
+                                                            float* __restrict__ dbias_next, int rows, int E, float eps) {
+  __shared__ float s_dg[512], s_db[512], s_dn[512];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; s_dn[i] = 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   const int nv = E >> 2;
-  float4 adg[LN_MAX_V4], adb[LN_MAX_V4];
+  float4 adg[LN_MAX_V4], adb[LN_MAX_V4], adn[LN_MAX_V4];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) { adg[i] = make_float4(0, 0, 0, 0); adb[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    adg[i] = make_float4(0, 0, 0, 0); adb[i] = make_float4(0, 0, 0, 0); adn[i] = make_float4(0, 0, 0, 0);
+  }
 
   for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * E);
@@ -147,8 +149,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         if (dx_bf16) {
           // the bf16 copy feeds the NEXT residual branch's grads; DropPath scales that branch per sequence
           const float sc = bf16_seq_scale ? __ldg(bf16_seq_scale + (row >> 8)) : 1.0f;
-          reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * E)[c] =
-              make_uint2(pack_bf16x2(o.x * sc, o.y * sc), pack_bf16x2(o.z * sc, o.w * sc));
+          const uint2 pk = make_uint2(pack_bf16x2(o.x * sc, o.y * sc), pack_bf16x2(o.z * sc, o.w * sc));
+          reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * E)[c] = pk;
+          // column sums of the bf16 copy = gradient of the bias of the linear layer that consumes it as dY
+          adn[i].x += bf16lo(pk.x); adn[i].y += bf16hi(pk.x); adn[i].z += bf16lo(pk.y); adn[i].w += bf16hi(pk.y);
         }
       }
     }
@@ -161,12 +165,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       atomicAdd(&s_dg[4 * c + 2], adg[i].z); atomicAdd(&s_dg[4 * c + 3], adg[i].w);
       atomicAdd(&s_db[4 * c + 0], adb[i].x); atomicAdd(&s_db[4 * c + 1], adb[i].y);
       atomicAdd(&s_db[4 * c + 2], adb[i].z); atomicAdd(&s_db[4 * c + 3], adb[i].w);
+      if (dbias_next) {
+        atomicAdd(&s_dn[4 * c + 0], adn[i].x); atomicAdd(&s_dn[4 * c + 1], adn[i].y);
+        atomicAdd(&s_dn[4 * c + 2], adn[i].z); atomicAdd(&s_dn[4 * c + 3], adn[i].w);
+      }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
     atomicAdd(dgamma + i, s_dg[i]);
     atomicAdd(dbeta + i, s_db[i]);
+    if (dbias_next) atomicAdd(dbias_next + i, s_dn[i]);
   }
 }
 
@@ -368,16 +377,16 @@ extern "C" int ccd_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int ccd_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_is_bf16, const float* resid,
                                  float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, const float* bf16_seq_scale,
-                                 int rows, int E, float eps, void* stream) {
+                                 float* dbias_next, int rows, int E, float eps, void* stream) {
   if (!x || !gamma || !dy || !dgamma || !dbeta || rows <= 0 || (E & 3) || E > 512) return CCD_ERR_ARG;
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (dy_is_bf16)
     layernorm_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma,
-                                                                          dbeta, bf16_seq_scale, rows, E, eps);
+                                                                          dbeta, bf16_seq_scale, dbias_next, rows, E, eps);
   else
     layernorm_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma,
-                                                                           dbeta, bf16_seq_scale, rows, E, eps);
+                                                                           dbeta, bf16_seq_scale, dbias_next, rows, E, eps);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }

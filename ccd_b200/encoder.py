@@ -236,8 +236,9 @@ class VitFn(torch.autograd.Function):
         i_norm = 3 + 12 * depth
         d_tokens = d_tokens.contiguous().float().view(T, E) if d_tokens is not None else zero_like_tokens()
         last_scale = drop[2 * depth - 1] if drop is not None else None
+        # every LN backward also accumulates the column sums of its bf16 output = bias gradient of the layer fed by it
         dx, dxb = ops.layernorm_bwd(ctx.x_final, params[i_norm].detach(), d_tokens, None, grads[i_norm], grads[i_norm + 1],
-                                    bf16_seq_scale=last_scale)
+                                    bf16_seq_scale=last_scale, dbias_next=grads[3 + 12 * (depth - 1) + 11])
         for l in reversed(range(depth)):
             sv = ctx.saved[l]
             x, xn, qkv, o, lse, x2, xn2, hpre, hact = sv[:9]
@@ -252,20 +253,21 @@ class VitFn(torch.autograd.Function):
                 if dt is not None:
                     dt = dt.contiguous().float().view(T, E)
                     gi = i_norm + 2 + 2 * i
-                    dx, dxb = ops.layernorm_bwd(sv[9], params[gi].detach(), dt, dx, grads[gi], grads[gi + 1], bf16_seq_scale=ds_mlp)
+                    grads[pi + 11].zero_()        # fc2.bias sums restart: this tap re-derives the bf16 copy
+                    dx, dxb = ops.layernorm_bwd(sv[9], params[gi].detach(), dt, dx, grads[gi], grads[gi + 1], bf16_seq_scale=ds_mlp,
+                                                dbias_next=grads[pi + 11])
             # ---- MLP branch: x3 = x2 + s*(gelu(xn2 W1^T + b1) W2^T + b2);  dxb = s * dx (bf16) ----
-            ops.linear_wgrad(dxb, hact, grads[pi + 10])
-            ops.colsum_bf16(dxb, grads[pi + 11])
+            ops.linear_wgrad(dxb, hact, grads[pi + 10])             # fc2.bias grad came from the producer of dxb
             dh = torch.empty(T, 4 * E, **b16)
             ops.linear_dgrad(dxb, wfc2, ops.EPI_DGELU, dh, hpre)
             ops.linear_wgrad(dh, xn2, grads[pi + 8])
             ops.colsum_bf16(dh, grads[pi + 9])
             dxn2 = torch.empty(T, E, **b16)
             ops.linear_dgrad(dh, wfc1, ops.EPI_BF16, dxn2)
-            dx2, dx2b = ops.layernorm_bwd(x2, g2, dxn2, dx, grads[pi + 6], grads[pi + 7], bf16_seq_scale=ds_attn)
+            dx2, dx2b = ops.layernorm_bwd(x2, g2, dxn2, dx, grads[pi + 6], grads[pi + 7], bf16_seq_scale=ds_attn,
+                                          dbias_next=grads[pi + 5])
             # ---- attention branch: x2 = x + s*(attn(xn) Wp^T + bp) ----
-            ops.linear_wgrad(dx2b, o, grads[pi + 4])
-            ops.colsum_bf16(dx2b, grads[pi + 5])
+            ops.linear_wgrad(dx2b, o, grads[pi + 4])                # proj.bias grad came from the LN2 backward above
             d_o = torch.empty(T, E, **b16)
             ops.linear_dgrad(dx2b, wproj, ops.EPI_BF16, d_o)
             dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, n, H)
@@ -277,11 +279,11 @@ class VitFn(torch.autograd.Function):
             if drop is not None and l > 0:
                 prev_scale = drop[2 * l - 1]
             # NB: a tap LN backward (if any) sits between this block and the previous one and re-derives the bf16 copy
-            dx, dxb = ops.layernorm_bwd(x, g1, dxn, dx2, grads[pi], grads[pi + 1], bf16_seq_scale=prev_scale)
+            dx, dxb = ops.layernorm_bwd(x, g1, dxn, dx2, grads[pi], grads[pi + 1], bf16_seq_scale=prev_scale,
+                                        dbias_next=(grads[pi - 12 + 11] if l > 0 else grads[2]))
             ctx.saved[l] = None
         # ---- patch embed: x0 = cols Wp^T + b + P_eff ----
-        ops.linear_wgrad(dxb, ctx.cols, d_wpatch)
-        ops.colsum_bf16(dxb, grads[2])
+        ops.linear_wgrad(dxb, ctx.cols, d_wpatch)                   # patch bias grad came from block 0's LN1 backward
         grads[1].copy_(d_wpatch[:, :48].reshape(grads[1].shape))
         dpos_eff = torch.zeros(GRID_TOKENS * E, dtype=torch.float32, device=dev)
         ops.colsum_f32(dx.view(n, GRID_TOKENS * E), dpos_eff)

@@ -147,13 +147,13 @@ def layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=False):
     return yb, yf
 
 
-def layernorm_bwd(x, gamma, dy, resid, dgamma, dbeta, want_f32=True, want_bf16=True, bf16_seq_scale=None):
+def layernorm_bwd(x, gamma, dy, resid, dgamma, dbeta, want_f32=True, want_bf16=True, bf16_seq_scale=None, dbias_next=None):
     rows, E = x.shape
     assert dy.is_contiguous() and dy.shape == x.shape
     dxf = torch.empty(rows, E, dtype=torch.float32, device=x.device) if want_f32 else None
     dxb = torch.empty(rows, E, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     _call("ccd_layernorm_bwd", _p(x), _p(gamma), _p(dy), 1 if dy.dtype == torch.bfloat16 else 0, _p(resid), _p(dxf), _p(dxb),
-          _p(dgamma), _p(dbeta), _p(bf16_seq_scale), rows, E, LN_EPS, _s())
+          _p(dgamma), _p(dbeta), _p(bf16_seq_scale), _p(dbias_next), rows, E, LN_EPS, _s())
     return dxf, dxb
 
 

@@ -50,10 +50,12 @@ int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* l
 /* LayerNorm (eps 1e-6) over f32 rows -> bf16 and/or f32.  Block.norm1/norm2, norm, norm_seg: vision_transformer.py:108-110,247,250 */
 int ccd_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, int rows, int E,
                       float eps, void* stream);
-/* dx = LN'(dy) + resid; writes f32 and/or bf16; dgamma/dbeta accumulate (caller zero-fills). */
+/* dx = LN'(dy) + resid; writes f32 and/or bf16 (bf16 copy scaled per sequence by bf16_seq_scale = DropPath of the
+ * branch it feeds); dgamma/dbeta accumulate (caller zero-fills); dbias_next (optional) accumulates the column sums of the
+ * bf16 copy = bias gradient of the linear layer that consumes it as dY. */
 int ccd_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_is_bf16, const float* resid, float* dx_f32,
-                      void* dx_bf16, float* dgamma, float* dbeta, const float* bf16_seq_scale, int rows, int E, float eps,
-                      void* stream);
+                      void* dx_bf16, float* dgamma, float* dbeta, const float* bf16_seq_scale, float* dbias_next, int rows,
+                      int E, float eps, void* stream);
 
 /* out[c] += sum_r x[r,c]  (bias gradients / teacher-centre batch sum Dino/loss/Dino_loss.py:138); out zero-filled by caller */
 int ccd_colsum_bf16(const void* x, float* out, int rows, int cols, void* stream);
