@@ -254,27 +254,26 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM walks a list of work items (m-block, n-block, k-slice).  The per-CTA fixed
-// costs of the one-tile kernel above (launch, barrier init, TMEM alloc, TMA pipeline fill, epilogue drain) dominate
-// when K = 384 gives only 6 k-blocks per tile; here
-//   * the TMA producer streams k-blocks continuously across tile boundaries through a 6-stage ring (the tile rate is
-//     set by the operand bytes in flight per SM: 192 KB per tile at K=384 against ~1.3 us of L2/HBM latency),
-//   * four 128-column TMEM accumulators decouple the MMA issuer from the epilogue,
-//   * two epilogue warpgroups alternate tiles; per 32-column chunk: TMEM -> regs -> 4 KB swizzled smem transpose ->
-//     4 rows x 128 B per warp instruction of global I/O with the fused epilogue (auxiliary operands of the whole chunk
-//     are requested before the transpose).
-// 320 threads: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1.
+// Persistent variant: one CTA per SM walks a list of work items (m-block, n-block, k-slice).  Measured on B200
+// (profiles/): with 128x128 tiles and K = 384 the one-tile kernel above spends ~7 us of CTA lifetime on 0.8 us of MMA,
+// and a persistent 128x128 version is limited by the SINGLE producer thread (a k-block needs 2-4 cp.async.bulk.tensor
+// issues against 256 MMA cycles).  Hence:
+//   * 128 x BN tiles with BN in {128, 192, 256} (picked so that BN divides N): 384-512 MMA cycles per k-block,
+//   * TWO producer warps (A operand / B operand) streaming k-blocks continuously across tile boundaries,
+//   * two TMEM accumulators (2 x BN <= 512 columns) so the MMA issuer runs one tile ahead of the epilogue,
+//   * two epilogue warpgroups alternating tiles; per 32-column chunk: TMEM -> regs -> 4 KB swizzled smem transpose ->
+//     4 rows x 128 B per warp instruction of global I/O with the fused epilogue (auxiliary operands of the chunk are
+//     requested before the transpose).
+// 352 threads: warp 0 TMA(A), warp 1 MMA, warp 2 TMA(B), warps 3-6 epilogue group 0, warps 7-10 epilogue group 1.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int PG_BN = 128;
-constexpr int PG_STAGE_BYTES = (GEMM_BM + PG_BN) * GEMM_BK * 2;   // 32 KB
-constexpr int PG_ACC = 4;                                          // TMEM accumulator buffers (4 x 128 columns)
+constexpr int PG_THREADS = 352;
 constexpr int PG_STAGING = 32 * 32 * 4;                            // 4 KB per epilogue warp: one 32x32 fp32 chunk
-// NG epilogue warpgroups: 2 for the light epilogues (6-stage ring = 192 KB of operands in flight per SM), 4 for the
-// GELU / GELU' epilogues, which are instruction-issue bound (~20 instructions per output element) with fewer warps.
-template <int NG> struct PgCfg {
-  static constexpr int STAGES = (NG == 2) ? 6 : 5;
-  static constexpr int THREADS = 64 + NG * 128;
-  static constexpr int SMEM = STAGES * PG_STAGE_BYTES + NG * 4 * PG_STAGING + 256 + 1024;
+template <int BN> struct PgCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;            // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;                 // 16 / 24 / 32 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 6 : 4;               // 192 / 160 / 192 KB of operands in flight
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 8 * PG_STAGING + 256 + 1024;
 };
 
 struct PgWork {
@@ -321,30 +320,31 @@ __device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, i
   }
 }
 
-template <int EPI, int NG>
-__global__ void __launch_bounds__(PgCfg<NG>::THREADS, 1)
+template <int EPI, int BN>
+__global__ void __launch_bounds__(PG_THREADS, 1)
 gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const GemmParams p_in, const PgWork wk) {
+  using Cfg = PgCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int PG_STAGES = PgCfg<NG>::STAGES;
-  uint8_t* staging = smem + PG_STAGES * PG_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + NG * 4 * PG_STAGING);
-  uint64_t* empty_bar = full_bar + PG_STAGES;
-  uint64_t* tmem_full = empty_bar + PG_STAGES;    // [PG_ACC]
-  uint64_t* tmem_empty = tmem_full + PG_ACC;      // [PG_ACC]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + PG_ACC);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 8 * PG_STAGING);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kb_total = (p_in.K + GEMM_BK - 1) / GEMM_BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PG_STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);                  // one arrive.expect_tx per producer warp
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < PG_ACC; ++a) {
+    for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 128);
     }
@@ -361,34 +361,39 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer: one continuous k-block stream over all items of this CTA =====================
+  if (warp == 0 || warp == 2) {
+    // ===================== TMA producers: warp 0 streams A, warp 2 streams B, continuously over all items =====================
     if (lane == 0) {
+      const bool is_a = (warp == 0);
       uint32_t kbc = 0;   // running k-block counter -> ring slot / phase
       for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x) {
         const int z = item / wk.n_tiles, tile = item - z * wk.n_tiles;
-        const int m0 = (tile / wk.n_tiles_n) * GEMM_BM, n0 = (tile % wk.n_tiles_n) * PG_BN;
+        const int m0 = (tile / wk.n_tiles_n) * GEMM_BM, n0 = (tile % wk.n_tiles_n) * BN;
         const int kb_begin = z * p_in.kb_per_split;
         const int nkb = min(kb_total, kb_begin + p_in.kb_per_split) - kb_begin;
         for (int i = 0; i < nkb; ++i, ++kbc) {
-          const int s = kbc % PG_STAGES;
-          const uint32_t ph = (kbc / PG_STAGES) & 1;
+          const int s = kbc % STAGES;
+          const uint32_t ph = (kbc / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], PG_STAGE_BYTES);
-          uint8_t* sa = smem + s * PG_STAGE_BYTES;
-          uint8_t* sb = sa + GEMM_BM * GEMM_BK * 2;
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
           const int k0 = (kb_begin + i) * GEMM_BK;
-          if (!p_in.a_mn) {
-            tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+          if (is_a) {
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES);
+            if (!p_in.a_mn) {
+              tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+            } else {
+              tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
+              tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
+            }
           } else {
-            tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
-            tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
-          }
-          if (!p_in.b_mn) {
-            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
-          } else {
-            tma_load_2d(sb, &tmB, &full_bar[s], n0, k0);
-            tma_load_2d(sb + 8192, &tmB, &full_bar[s], n0 + 64, k0);
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES);
+            if (!p_in.b_mn) {
+              tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
+            }
           }
         }
       }
@@ -396,24 +401,24 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, PG_BN, p_in.a_mn, p_in.b_mn);
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, p_in.a_mn, p_in.b_mn);
       uint32_t kbc = 0;
       int it = 0;
       for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x, ++it) {
         const int z = item / wk.n_tiles;
         const int kb_begin = z * p_in.kb_per_split;
         const int nkb = min(kb_total, kb_begin + p_in.kb_per_split) - kb_begin;
-        const int acc = it % PG_ACC;
-        mbar_wait(&tmem_empty[acc], ((it / PG_ACC) & 1) ^ 1);     // epilogue drained this accumulator
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);         // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * PG_BN;
+        const uint32_t d_tmem = tmem_base + acc * BN;
         for (int i = 0; i < nkb; ++i, ++kbc) {
-          const int s = kbc % PG_STAGES;
-          const uint32_t ph = (kbc / PG_STAGES) & 1;
+          const int s = kbc % STAGES;
+          const uint32_t ph = (kbc / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * PG_STAGE_BYTES);
-          const uint32_t b_addr = a_addr + GEMM_BM * GEMM_BK * 2;
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = p_in.a_mn ? umma_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
@@ -429,25 +434,25 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: group g takes items it = g, g+NG, ... of this CTA =====================
-    const int g = (warp - 2) >> 2;
-    const int q = warp & 3;
-    float* stage = reinterpret_cast<float*>(staging + (warp - 2) * PG_STAGING);
+    // ===================== epilogue: group g takes items it = g, g+2, ... of this CTA (accumulator it & 1 == g) =====================
+    const int g = (warp - 3) >> 2;
+    const int q = warp & 3;                                       // TMEM lane quarter this warp may read
+    float* stage = reinterpret_cast<float*>(staging + (warp - 3) * PG_STAGING);
     int it = 0;
     for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x, ++it) {
-      if ((it % NG) != g) continue;
+      if ((it & 1) != g) continue;
       GemmParams p = p_in;
       const int z = item / wk.n_tiles, tile = item - z * wk.n_tiles;
       if (z != 0) p.bias = nullptr;
-      const int m0 = (tile / wk.n_tiles_n) * GEMM_BM, n0 = (tile % wk.n_tiles_n) * PG_BN;
-      const int acc = it % PG_ACC;
+      const int m0 = (tile / wk.n_tiles_n) * GEMM_BM, n0 = (tile % wk.n_tiles_n) * BN;
+      const int acc = it & 1;
       const int row_base = m0 + q * 32;
       const int nrows = max(0, min(32, p.M - row_base));
       const int sub_row = lane >> 3, sub_chunk = lane & 7;          // phase 2: 4 rows x 8 sixteen-byte chunks per instruction
-      mbar_wait(&tmem_full[acc], (it / PG_ACC) & 1);
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < PG_BN / 32; ++c) {
+      for (int c = 0; c < BN / 32; ++c) {
         const int col = n0 + c * 32 + 4 * sub_chunk;
         const bool col_ok = col < p.N;
         // auxiliary operands + bias of this chunk are requested first: their latency hides behind the transpose
@@ -458,9 +463,9 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * PG_BN + c * 32), raw);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), raw);
         tmem_wait_ld();
-        if (c == PG_BN / 32 - 1) {               // accumulator fully read: hand it back to the MMA issuer
+        if (c == BN / 32 - 1) {                  // accumulator fully read: hand it back to the MMA issuer
           tc_fence_before();
           mbar_arrive(&tmem_empty[acc]);
         }
@@ -489,27 +494,44 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 
 static int g_gemm_variant = 1;   // 1 = persistent (default), 0 = one tile per CTA
 
-template <int EPI, int NG>
+template <int EPI, int BN>
 static int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits,
                                   cudaStream_t stream) {
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
-    CCD_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<EPI, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        PgCfg<NG>::SMEM));
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        PgCfg<BN>::SMEM));
     int dev = 0;
     CCD_CUDA_CHECK(cudaGetDevice(&dev));
     CCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
   PgWork wk;
-  wk.n_tiles_n = (p.N + PG_BN - 1) / PG_BN;
+  wk.n_tiles_n = (p.N + BN - 1) / BN;
   wk.n_tiles = wk.n_tiles_n * ((p.M + GEMM_BM - 1) / GEMM_BM);
   wk.n_items = wk.n_tiles * splits;
   const int grid = wk.n_items < num_sms ? wk.n_items : num_sms;
-  gemm_umma_persistent_kernel<EPI, NG><<<grid, PgCfg<NG>::THREADS, PgCfg<NG>::SMEM, stream>>>(tmA, tmB, p, wk);
+  gemm_umma_persistent_kernel<EPI, BN><<<grid, PG_THREADS, PgCfg<BN>::SMEM, stream>>>(tmA, tmB, p, wk);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
+}
+
+template <int EPI>
+static int dispatch_gemm_persistent(const void* A, const void* B, const GemmParams& p, int splits, cudaStream_t stream) {
+  // BN is the widest of {256, 192, 128} that divides N (ragged N falls back to 128 with column masking)
+  const int bn = (p.N % 256 == 0) ? 256 : (p.N % 192 == 0) ? 192 : 128;
+  CUtensorMap tmA, tmB;
+  bool ok;
+  if (!p.a_mn) ok = get_tmap_bf16_2d(&tmA, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, GEMM_BM, 64);
+  else         ok = get_tmap_bf16_2d(&tmA, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.M, 64, 64);
+  if (!ok) return CCD_ERR_TMAP;
+  if (!p.b_mn) ok = get_tmap_bf16_2d(&tmB, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)bn, 64);
+  else         ok = get_tmap_bf16_2d(&tmB, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.N, 64, 64);
+  if (!ok) return CCD_ERR_TMAP;
+  if (bn == 256) return launch_gemm_persistent<EPI, 256>(tmA, tmB, p, splits, stream);
+  if (bn == 192) return launch_gemm_persistent<EPI, 192>(tmA, tmB, p, splits, stream);
+  return launch_gemm_persistent<EPI, 128>(tmA, tmB, p, splits, stream);
 }
 
 template <int EPI, int BN>
@@ -548,6 +570,20 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
   int kb_per = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per - 1) / kb_per;  // every z slice gets >= 1 k-block
 
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0; p.kb_per_split = kb_per;
+  p.bias = bias; p.out0 = out0; p.out1 = out1; p.aux = aux; p.ldc = ldc; p.atomic = (splits > 1) ? 1 : 0;
+  p.seq_scale = seq_scale;
+  if (g_gemm_variant == 1) {
+    switch (epi) {
+      case EPI_BF16:  return dispatch_gemm_persistent<EPI_BF16>(A, B, p, splits, stream);
+      case EPI_GELU:  return dispatch_gemm_persistent<EPI_GELU>(A, B, p, splits, stream);
+      case EPI_RESID: return dispatch_gemm_persistent<EPI_RESID>(A, B, p, splits, stream);
+      case EPI_F32:   return dispatch_gemm_persistent<EPI_F32>(A, B, p, splits, stream);
+      case EPI_DGELU: return dispatch_gemm_persistent<EPI_DGELU>(A, B, p, splits, stream);
+      case EPI_POS:   return dispatch_gemm_persistent<EPI_POS>(A, B, p, splits, stream);
+    }
+  }
   constexpr int BN = 128;
   CUtensorMap tmA, tmB;
   bool ok;
@@ -559,20 +595,6 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
   else       ok = get_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)N, 64, 64);
   if (!ok) return CCD_ERR_TMAP;
 
-  GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0; p.kb_per_split = kb_per;
-  p.bias = bias; p.out0 = out0; p.out1 = out1; p.aux = aux; p.ldc = ldc; p.atomic = (splits > 1) ? 1 : 0;
-  p.seq_scale = seq_scale;
-  if (g_gemm_variant == 1) {
-    switch (epi) {
-      case EPI_BF16:  return launch_gemm_persistent<EPI_BF16, 2>(tmA, tmB, p, splits, stream);
-      case EPI_GELU:  return launch_gemm_persistent<EPI_GELU, 4>(tmA, tmB, p, splits, stream);
-      case EPI_RESID: return launch_gemm_persistent<EPI_RESID, 2>(tmA, tmB, p, splits, stream);
-      case EPI_F32:   return launch_gemm_persistent<EPI_F32, 2>(tmA, tmB, p, splits, stream);
-      case EPI_DGELU: return launch_gemm_persistent<EPI_DGELU, 4>(tmA, tmB, p, splits, stream);
-      case EPI_POS:   return launch_gemm_persistent<EPI_POS, 2>(tmA, tmB, p, splits, stream);
-    }
-  }
   switch (epi) {
     case EPI_BF16:  return launch_gemm<EPI_BF16, BN>(tmA, tmB, p, splits, stream);
     case EPI_GELU:  return launch_gemm<EPI_GELU, BN>(tmA, tmB, p, splits, stream);

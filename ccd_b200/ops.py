@@ -90,8 +90,16 @@ def gemm(A, B, M, N, K, a_mn=0, b_mn=0, epi=EPI_BF16, bias=None, out0=None, out1
     return out0
 
 
+def gemm_bn(n):
+    """N-tile of the persistent GEMM (mirrors dispatch_gemm_persistent in csrc/gemm_umma.cu)."""
+    return 256 if n % 256 == 0 else 192 if n % 192 == 0 else 128
+
+
 def wgrad_splits(n_out, k_in, t_rows):
-    tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+    """Split-K factor of a weight-gradient GEMM dW[n_out, k_in]: enough (tile, k-slice) work items for two rounds of the
+    148 persistent CTAs."""
+    bn = gemm_bn(k_in)
+    tiles = ((n_out + 127) // 128) * ((k_in + bn - 1) // bn)
     kb = (t_rows + 63) // 64
     return max(1, min(kb, (296 + tiles - 1) // tiles))
 

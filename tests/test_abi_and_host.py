@@ -62,7 +62,7 @@ def test_wgrad_split_plan_and_chunk_table():
     from ccd_b200 import ops
     assert ops.wgrad_splits(65536, 256, 4352) == 1
     s = ops.wgrad_splits(384, 1536, 131072)
-    assert 1 < s <= 2048 and s * 36 >= 296
+    assert 1 < s <= 2048 and s * 18 >= 296 and ops.gemm_bn(1152) == 192 and ops.gemm_bn(1536) == 256 and ops.gemm_bn(200) == 128
     tab = ops.ChunkTable()
     a = [torch.zeros(70000), torch.zeros(5)]
     b = [torch.zeros(70000, dtype=torch.bfloat16), torch.zeros(5, dtype=torch.bfloat16)]
