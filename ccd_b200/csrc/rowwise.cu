@@ -62,120 +62,139 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm backward (recomputes mean/rstd from x): dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) + resid,
-// g = dy*gamma.  dgamma/dbeta accumulated per CTA then atomically into [E] (pre-zeroed by the caller).
+// g = dy*gamma.  HBM-bound (16.. bytes per element in+out): each warp owns rows r, r+W, ...; the loads of the NEXT
+// row are issued before the reductions of the current one (software pipelining keeps ~2 rows of loads in flight
+// per warp), dgamma/dbeta/dbias partial sums live in a per-warp shared-memory slab (plain read-modify-write, no
+// atomics), reduced across the 8 warps at the end and added to global memory with one atomic per column per CTA.
+// NV = float4 per lane (E/128 rounded up): 2 (E=192), 3 (E=384), 4 (E=512).
 // ---------------------------------------------------------------------------------------------------------
-template <bool DY_BF16>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                            const void* __restrict__ dy_, const float* __restrict__ resid,
-                                                            float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            const float* __restrict__ bf16_seq_scale,
-                                                            float* __restrict__ dbias_next, int rows, int E, float eps) {
-  __shared__ float s_dg[512], s_db[512], s_dn[512];
-  for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; s_dn[i] = 0.f; }
-  __syncthreads();
+template <bool DY_BF16, int NV>
+struct LnRow {
+  float4 x[NV];
+  uint4 dy[NV];     // DY_BF16: .x/.y hold 4 bf16; else 4 floats
+  float4 rs[NV];
+};
+
+template <bool DY_BF16, int NV>
+__device__ __forceinline__ void ln_load_row(LnRow<DY_BF16, NV>& r, const float* __restrict__ x, const void* __restrict__ dy_,
+                                            const float* __restrict__ resid, int row, int E, int nv, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      r.x[i] = reinterpret_cast<const float4*>(x + (size_t)row * E)[c];
+      if constexpr (DY_BF16) {
+        const uint2 pk = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (size_t)row * E)[c];
+        r.dy[i] = make_uint4(pk.x, pk.y, 0u, 0u);
+      } else {
+        r.dy[i] = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * E)[c];
+      }
+      r.rs[i] = resid ? reinterpret_cast<const float4*>(resid + (size_t)row * E)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+template <bool DY_BF16, int NV>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const void* __restrict__ dy_, const float* __restrict__ resid,
+                                                               float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               const float* __restrict__ bf16_seq_scale,
+                                                               float* __restrict__ dbias_next, int rows, int E, float eps) {
+  extern __shared__ float ln_acc[];                 // [8 warps][3][E]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int warps_total = gridDim.x * 8;
   const int nv = E >> 2;
-  float4 adg[LN_MAX_V4], adb[LN_MAX_V4], adn[LN_MAX_V4];
+  float* my = ln_acc + (size_t)wib * 3 * E;
+  for (int i = lane; i < 3 * E; i += 32) my[i] = 0.f;
+  __syncwarp();
+  float4 gm[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    adg[i] = make_float4(0, 0, 0, 0); adb[i] = make_float4(0, 0, 0, 0); adn[i] = make_float4(0, 0, 0, 0);
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    gm[i] = (c < nv) ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  const float inv_e = 1.0f / (float)E;
 
-  for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * E);
-    float4 v[LN_MAX_V4], d[LN_MAX_V4], rs[LN_MAX_V4], g[LN_MAX_V4];
-    // issue every global load of the row up front (x, dy, residual gradient): the reductions below then overlap
-    // with the loads of the other warps instead of serialising three DRAM round trips per row
-#pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
-      const int c = lane + i * 32;
-      if (c < nv) {
-        v[i] = xr[c];
-        if constexpr (DY_BF16) {
-          const uint2 pk = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (size_t)row * E)[c];
-          d[i] = make_float4(bf16lo(pk.x), bf16hi(pk.x), bf16lo(pk.y), bf16hi(pk.y));
-        } else {
-          d[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * E)[c];
-        }
-        rs[i] = resid ? reinterpret_cast<const float4*>(resid + (size_t)row * E)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
+  int row = blockIdx.x * 8 + wib;
+  LnRow<DY_BF16, NV> cur, nxt;
+  if (row < rows) ln_load_row<DY_BF16, NV>(cur, x, dy_, resid, row, E, nv, lane);
+  for (; row < rows; row += warps_total) {
+    const int next_row = row + warps_total;
+    if (next_row < rows) ln_load_row<DY_BF16, NV>(nxt, x, dy_, resid, next_row, E, nv, lane);
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
-      const int c = lane + i * 32;
-      if (c < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
-    }
-    const float mean = warp_sum(s) / (float)E;
+    for (int i = 0; i < NV; ++i)
+      if (lane + i * 32 < nv) s += cur.x[i].x + cur.x[i].y + cur.x[i].z + cur.x[i].w;
+    const float mean = warp_sum(s) * inv_e;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
-      const int c = lane + i * 32;
-      if (c < nv) {
-        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-        q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    for (int i = 0; i < NV; ++i)
+      if (lane + i * 32 < nv) {
+        cur.x[i].x -= mean; cur.x[i].y -= mean; cur.x[i].z -= mean; cur.x[i].w -= mean;
+        q += cur.x[i].x * cur.x[i].x + cur.x[i].y * cur.x[i].y + cur.x[i].z * cur.x[i].z + cur.x[i].w * cur.x[i].w;
       }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
+    const float rstd = rsqrtf(warp_sum(q) * inv_e + eps);
     float m1 = 0.f, m2 = 0.f;
+    float4 g[NV];
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
-        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
-        adg[i].x += d[i].x * v[i].x; adg[i].y += d[i].y * v[i].y; adg[i].z += d[i].z * v[i].z; adg[i].w += d[i].w * v[i].w;
-        adb[i].x += d[i].x; adb[i].y += d[i].y; adb[i].z += d[i].z; adb[i].w += d[i].w;
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        g[i] = make_float4(d[i].x * gm.x, d[i].y * gm.y, d[i].z * gm.z, d[i].w * gm.w);
+        float4 d;
+        if constexpr (DY_BF16) d = make_float4(bf16lo(cur.dy[i].x), bf16hi(cur.dy[i].x), bf16lo(cur.dy[i].y), bf16hi(cur.dy[i].y));
+        else d = make_float4(__uint_as_float(cur.dy[i].x), __uint_as_float(cur.dy[i].y), __uint_as_float(cur.dy[i].z), __uint_as_float(cur.dy[i].w));
+        cur.x[i].x *= rstd; cur.x[i].y *= rstd; cur.x[i].z *= rstd; cur.x[i].w *= rstd;   // xhat
+        float4* ag = reinterpret_cast<float4*>(my) + c;                 // dgamma partial
+        float4* ab = reinterpret_cast<float4*>(my + E) + c;             // dbeta partial
+        float4 t = *ag;
+        t.x += d.x * cur.x[i].x; t.y += d.y * cur.x[i].y; t.z += d.z * cur.x[i].z; t.w += d.w * cur.x[i].w;
+        *ag = t;
+        t = *ab;
+        t.x += d.x; t.y += d.y; t.z += d.z; t.w += d.w;
+        *ab = t;
+        g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
         m1 += g[i].x + g[i].y + g[i].z + g[i].w;
-        m2 += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+        m2 += g[i].x * cur.x[i].x + g[i].y * cur.x[i].y + g[i].z * cur.x[i].z + g[i].w * cur.x[i].w;
       }
     }
-    m1 = warp_sum(m1) / (float)E;
-    m2 = warp_sum(m2) / (float)E;
+    m1 = warp_sum(m1) * inv_e;
+    m2 = warp_sum(m2) * inv_e;
+    const float sc = bf16_seq_scale ? __ldg(bf16_seq_scale + (row >> 8)) : 1.0f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
         float4 o;
-        o.x = rstd * (g[i].x - m1 - v[i].x * m2) + rs[i].x;
-        o.y = rstd * (g[i].y - m1 - v[i].y * m2) + rs[i].y;
-        o.z = rstd * (g[i].z - m1 - v[i].z * m2) + rs[i].z;
-        o.w = rstd * (g[i].w - m1 - v[i].w * m2) + rs[i].w;
+        o.x = rstd * (g[i].x - m1 - cur.x[i].x * m2) + cur.rs[i].x;
+        o.y = rstd * (g[i].y - m1 - cur.x[i].y * m2) + cur.rs[i].y;
+        o.z = rstd * (g[i].z - m1 - cur.x[i].z * m2) + cur.rs[i].z;
+        o.w = rstd * (g[i].w - m1 - cur.x[i].w * m2) + cur.rs[i].w;
         if (dx_f32) reinterpret_cast<float4*>(dx_f32 + (size_t)row * E)[c] = o;
         if (dx_bf16) {
           // the bf16 copy feeds the NEXT residual branch's grads; DropPath scales that branch per sequence
-          const float sc = bf16_seq_scale ? __ldg(bf16_seq_scale + (row >> 8)) : 1.0f;
           const uint2 pk = make_uint2(pack_bf16x2(o.x * sc, o.y * sc), pack_bf16x2(o.z * sc, o.w * sc));
           reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * E)[c] = pk;
-          // column sums of the bf16 copy = gradient of the bias of the linear layer that consumes it as dY
-          adn[i].x += bf16lo(pk.x); adn[i].y += bf16hi(pk.x); adn[i].z += bf16lo(pk.y); adn[i].w += bf16hi(pk.y);
+          if (dbias_next) {   // column sums of the bf16 copy = bias gradient of the linear layer that consumes it as dY
+            float4* an = reinterpret_cast<float4*>(my + 2 * E) + c;
+            float4 t = *an;
+            t.x += bf16lo(pk.x); t.y += bf16hi(pk.x); t.z += bf16lo(pk.y); t.w += bf16hi(pk.y);
+            *an = t;
+          }
         }
       }
     }
-  }
-#pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int c = lane + i * 32;
-    if (c < nv) {
-      atomicAdd(&s_dg[4 * c + 0], adg[i].x); atomicAdd(&s_dg[4 * c + 1], adg[i].y);
-      atomicAdd(&s_dg[4 * c + 2], adg[i].z); atomicAdd(&s_dg[4 * c + 3], adg[i].w);
-      atomicAdd(&s_db[4 * c + 0], adb[i].x); atomicAdd(&s_db[4 * c + 1], adb[i].y);
-      atomicAdd(&s_db[4 * c + 2], adb[i].z); atomicAdd(&s_db[4 * c + 3], adb[i].w);
-      if (dbias_next) {
-        atomicAdd(&s_dn[4 * c + 0], adn[i].x); atomicAdd(&s_dn[4 * c + 1], adn[i].y);
-        atomicAdd(&s_dn[4 * c + 2], adn[i].z); atomicAdd(&s_dn[4 * c + 3], adn[i].w);
-      }
-    }
+    cur = nxt;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    atomicAdd(dgamma + i, s_dg[i]);
-    atomicAdd(dbeta + i, s_db[i]);
-    if (dbias_next) atomicAdd(dbias_next + i, s_dn[i]);
+  for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += ln_acc[(size_t)w * 3 * E + i];
+    if (i < E) atomicAdd(dgamma + i, t);
+    else if (i < 2 * E) atomicAdd(dbeta + i - E, t);
+    else if (dbias_next) atomicAdd(dbias_next + i - 2 * E, t);
   }
 }
 
@@ -375,20 +394,41 @@ extern "C" int ccd_layernorm_fwd(const float* x, const float* gamma, const float
   return CCD_OK;
 }
 
+template <bool DY_BF16, int NV>
+static int launch_ln_bwd(const float* x, const float* gamma, const void* dy, const float* resid, float* dx_f32, void* dx_bf16,
+                         float* dgamma, float* dbeta, const float* bf16_seq_scale, float* dbias_next, int rows, int E, float eps,
+                         cudaStream_t stream) {
+  static bool attr_set = false;
+  const int smem = 8 * 3 * E * (int)sizeof(float);
+  if (!attr_set) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(layernorm_bwd_kernel<DY_BF16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 512 * 4));
+    attr_set = true;
+  }
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 2) blocks = 148 * 2;          // two resident CTAs per SM, each warp strides over its rows
+  layernorm_bwd_kernel<DY_BF16, NV><<<blocks, 256, smem, stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma, dbeta,
+                                                                  bf16_seq_scale, dbias_next, rows, E, eps);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
 extern "C" int ccd_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_is_bf16, const float* resid,
                                  float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, const float* bf16_seq_scale,
                                  float* dbias_next, int rows, int E, float eps, void* stream) {
   if (!x || !gamma || !dy || !dgamma || !dbeta || rows <= 0 || (E & 3) || E > 512) return CCD_ERR_ARG;
-  int blocks = (rows + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (dy_is_bf16)
-    layernorm_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma,
-                                                                          dbeta, bf16_seq_scale, dbias_next, rows, E, eps);
-  else
-    layernorm_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma,
-                                                                           dbeta, bf16_seq_scale, dbias_next, rows, E, eps);
-  CCD_LAUNCH_CHECK();
-  return CCD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nvl = (E / 4 + 31) / 32;
+#define CCD_LN_BWD(B, N) return launch_ln_bwd<B, N>(x, gamma, dy, resid, dx_f32, dx_bf16, dgamma, dbeta, bf16_seq_scale, dbias_next, rows, E, eps, s)
+  if (dy_is_bf16) {
+    if (nvl <= 2) CCD_LN_BWD(true, 2);
+    if (nvl == 3) CCD_LN_BWD(true, 3);
+    CCD_LN_BWD(true, 4);
+  } else {
+    if (nvl <= 2) CCD_LN_BWD(false, 2);
+    if (nvl == 3) CCD_LN_BWD(false, 3);
+    CCD_LN_BWD(false, 4);
+  }
+#undef CCD_LN_BWD
 }
 
 extern "C" int ccd_colsum_bf16(const void* x, float* out, int rows, int cols, void* stream) {
