@@ -455,6 +455,17 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int row_base = m0 + q * 32;
       const int nrows = max(0, min(32, p.M - row_base));
       const int sub_row = lane >> 3, sub_chunk = lane & 7;          // phase 2: 4 rows x 8 sixteen-byte chunks per instruction
+      // Pull this tile's auxiliary operand (residual stream / saved pre-activation) into L2 while the MMAs of the tile
+      // are still running: the per-chunk loads below then pay L2 instead of HBM latency.  Thread <-> row.
+      if constexpr (EPI == EPI_RESID || EPI == EPI_DGELU) {
+        constexpr int ES = (EPI == EPI_RESID) ? 4 : 2;
+        const int prow = row_base + lane;
+        if (prow < p.M) {
+          const char* base = reinterpret_cast<const char*>(p.aux) + ((size_t)prow * p.ldc + n0) * ES;
+          const int bytes = min(BN, p.N - n0) * ES;
+          for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+        }
+      }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1

@@ -6,6 +6,7 @@ smoke() and the tests run exactly the step BASELINE.json's metric is quoted on:
   -> per-parameter clip -> cancel last-layer grads (epoch < freeze_last_layer) -> AdamW -> teacher EMA.
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -39,8 +40,11 @@ class PretrainStep:
             if has_batchnorms(student):                                                                       # :96-101
                 student = nn.SyncBatchNorm.convert_sync_batchnorm(student)
                 self.student_module = student
+            # train.py:106 uses find_unused_parameters=True (cls_token and segmentation.conv_mla.* never get gradients);
+            # static_graph=True gives the same semantics without re-walking the autograd graph every iteration
             student = nn.parallel.DistributedDataParallel(student, device_ids=[self.device.index],
-                                                          find_unused_parameters=True)                        # :106
+                                                          find_unused_parameters=True,
+                                                          static_graph=os.environ.get("CCD_DDP_STATIC", "1") == "1")
         self.student, self.teacher = student, teacher
         teacher.backbone.load_state_dict(self.student_module.backbone.state_dict())                           # :109-110
         teacher.head.load_state_dict(self.student_module.head.state_dict())
