@@ -126,7 +126,8 @@ def linear_wgrad(dy_bf16, x_bf16, dw_f32_zeroed):
     return gemm(dy_bf16, x_bf16, N, K, T, 1, 1, EPI_F32, None, dw_f32_zeroed, None, None, dw_f32_zeroed.shape[1], sp)
 
 
-MHSA_FWD_VARIANT = int(__import__("os").environ.get("CCD_MHSA_FWD_VARIANT", "0"))
+# 2 = persistent kernel (default); 0 / 1 = one CTA per (sequence, head, query tile) with P in TMEM / in shared memory
+MHSA_FWD_VARIANT = int(__import__("os").environ.get("CCD_MHSA_FWD_VARIANT", "2"))
 
 
 def mhsa_fwd(qkv, S, H, want_lse=True, variant=None):
