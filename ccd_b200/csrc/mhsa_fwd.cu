@@ -349,32 +349,46 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
       const int s = w / p.H, h = w - s * p.H;
       mbar_wait(&s_full[t], ph);
       tc_fence_after();
+      // two 32-column TMEM loads in flight per wait (64-column chunks) in both passes
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int ch = 0; ch < ATT_N / 32; ++ch) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tS + lane_sel + ch * 32, raw);
+      for (int ch = 0; ch < ATT_N / 64; ++ch) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(tS + lane_sel + ch * 64, ra);
+        tmem_ld_32x32(tS + lane_sel + ch * 64 + 32, rb);
         tmem_wait_ld();
+        float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+        for (int j = 0; j < 32; ++j) {
+          m0 = fmaxf(m0, __uint_as_float(ra[j]));
+          m1 = fmaxf(m1, __uint_as_float(rb[j]));
+        }
+        mx = fmaxf(mx, fmaxf(m0, m1));
       }
       const float mc = mx * c;
-      float sum = 0.f;
+      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll 1
-      for (int ch = 0; ch < ATT_N / 32; ++ch) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tS + lane_sel + ch * 32, raw);
+      for (int ch = 0; ch < ATT_N / 64; ++ch) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(tS + lane_sel + ch * 64, ra);
+        tmem_ld_32x32(tS + lane_sel + ch * 64 + 32, rb);
         tmem_wait_ld();
-        uint32_t pk[16];
+        uint32_t pa[16], pb[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * j]), c, -mc));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * j + 1]), c, -mc));
-          pk[j] = pack_bf16x2(p0, p1);
-          sum += bf16lo(pk[j]) + bf16hi(pk[j]);
+          const float a0 = ex2_approx(fmaf(__uint_as_float(ra[2 * j]), c, -mc));
+          const float a1 = ex2_approx(fmaf(__uint_as_float(ra[2 * j + 1]), c, -mc));
+          const float b0 = ex2_approx(fmaf(__uint_as_float(rb[2 * j]), c, -mc));
+          const float b1 = ex2_approx(fmaf(__uint_as_float(rb[2 * j + 1]), c, -mc));
+          pa[j] = pack_bf16x2(a0, a1);
+          pb[j] = pack_bf16x2(b0, b1);
+          sum0 += bf16lo(pa[j]) + bf16hi(pa[j]);    // the rounded values: P V / sum(P) stays a convex combination
+          sum1 += bf16lo(pb[j]) + bf16hi(pb[j]);
         }
-        tmem_st_32x16(tS + lane_sel + ch * 16, pk);
+        tmem_st_32x16(tS + lane_sel + ch * 32, pa);        // P chunk (bf16 pairs) over S columns already consumed
+        tmem_st_32x16(tS + lane_sel + ch * 32 + 16, pb);
       }
+      const float sum = sum0 + sum1;
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
