@@ -26,6 +26,7 @@ struct MhsaBwdParams {
   const bf16* o;      // [T, E] forward output
   const bf16* d_o;    // [T, E]
   const float* lse2;  // [S, H, 256]
+  const float* delta; // [S, H, 256]  rowsum(O * dO), produced by mhsa_delta_kernel
   bf16* dqkv;         // [T, 3E]
   int E, H;
   float scale, scale_log2;
@@ -72,6 +73,27 @@ __device__ __forceinline__ void store_tmem_row64(uint32_t taddr, bf16* dst) {
       o.w = pack_bf16x2(__uint_as_float(raw[8 * g + 6]), __uint_as_float(raw[8 * g + 7]));
       *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = o;
     }
+  }
+}
+
+// delta[s,h,q] = sum_d O[q, h*64+d] * dO[q, h*64+d]: one warp per token row, 16-byte loads, 8 lanes per head.
+// (Inside the main kernel this prologue was ~30 % of the stall samples: 32 rows x 16 B per load instruction.)
+__global__ void __launch_bounds__(256) mhsa_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                                                         float* __restrict__ delta, int T, int E, int H) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const uint4* po = reinterpret_cast<const uint4*>(o + (size_t)row * E);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + (size_t)row * E);
+  const int nchunk = E >> 3;                       // 8 bf16 per 16-byte chunk; 8 chunks per head
+  const int s = row >> 8, q = row & 255;
+  for (int c0 = 0; c0 < nchunk; c0 += 32) {
+    const int c = c0 + lane;
+    float acc = (c < nchunk) ? dot8_bf16(po[c], pd[c]) : 0.f;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if ((lane & 7) == 0 && c < nchunk) delta[((size_t)s * H + (c >> 3)) * ATB_N + q] = acc;
   }
 }
 
@@ -181,17 +203,12 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;  // key row within tile j / query row in the epilogues
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    // delta[q] = sum_d O[q,d] dO[q,d]; lse2 -> smem   (256 threads <-> 256 query rows)
+    // delta[q] (precomputed, coalesced) and lse2 -> smem   (256 threads <-> 256 query rows)
     {
       const int rr = wg * 128 + r;
-      const bf16* po = p.o + ((size_t)row0 + rr) * p.E + h * ATB_D;
-      const bf16* pd = p.d_o + ((size_t)row0 + rr) * p.E + h * ATB_D;
-      float acc = 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        acc += dot8_bf16(*reinterpret_cast<const uint4*>(po + g * 8), *reinterpret_cast<const uint4*>(pd + g * 8));
-      sDelta[rr] = acc;
-      sLse[rr] = p.lse2[((size_t)s * p.H + h) * ATB_N + rr];
+      const size_t gi = ((size_t)s * p.H + h) * ATB_N + rr;
+      sDelta[rr] = p.delta[gi];
+      sLse[rr] = p.lse2[gi];
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float c = p.scale_log2;
@@ -258,10 +275,10 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 using namespace ccd;
 
 // C ABI -- see include/ccd_b200.h
-extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int S,
-                            int H, void* stream_) {
+extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, float* delta_ws, void* dqkv,
+                            int S, int H, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!qkv || !o || !d_o || !lse2 || !dqkv || S <= 0 || H <= 0) return CCD_ERR_ARG;
+  if (!qkv || !o || !d_o || !lse2 || !delta_ws || !dqkv || S <= 0 || H <= 0) return CCD_ERR_ARG;
   const int E = H * ATB_D;
   CUtensorMap tmQKV, tmDO;
   if (!get_tmap_bf16_2d(&tmQKV, qkv, (uint64_t)S * ATB_N, (uint64_t)3 * E, (uint64_t)3 * E, 128, 64)) return CCD_ERR_TMAP;
@@ -270,6 +287,7 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
   p.o = reinterpret_cast<const bf16*>(o);
   p.d_o = reinterpret_cast<const bf16*>(d_o);
   p.lse2 = lse2;
+  p.delta = delta_ws;
   p.dqkv = reinterpret_cast<bf16*>(dqkv);
   p.E = E;
   p.H = H;
@@ -281,6 +299,8 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
                                         MhsaBwdSmem::SMEM_BYTES));
     attr_set = true;
   }
+  mhsa_delta_kernel<<<(S * ATB_N + 7) / 8, 256, 0, stream>>>(p.o, p.d_o, delta_ws, S * ATB_N, E, H);
+  CCD_LAUNCH_CHECK();
   dim3 grid(H, S);
   mhsa_bwd_kernel<<<grid, ATB_THREADS, MhsaBwdSmem::SMEM_BYTES, stream>>>(tmQKV, tmDO, p);
   CCD_LAUNCH_CHECK();

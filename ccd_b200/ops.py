@@ -17,7 +17,7 @@ SLOTS = 26
 _CTYPE = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong}
 _FN = {}
 LAUNCHES = [0]     # number of kernels launched through the C ABI (bench.py reports it)
-KERNELS_PER_CALL = {"ccd_dino_ce_fwd": 2, "ccd_seg_ce_fwd": 2, "ccd_char_plan": 3}
+KERNELS_PER_CALL = {"ccd_dino_ce_fwd": 2, "ccd_seg_ce_fwd": 2, "ccd_char_plan": 3, "ccd_mhsa_bwd": 2}
 # bench.py roofline instrumentation: when a dict, every call of a listed entry point is bracketed by CUDA events on
 # the launching stream:  PROFILE = {"names": {"ccd_gemm_bf16", ...}, "events": []}
 PROFILE = None
@@ -143,7 +143,8 @@ def mhsa_fwd(qkv, S, H, want_lse=True, variant=None):
 
 def mhsa_bwd(qkv, o, d_o, lse, S, H):
     dqkv = torch.empty_like(qkv)
-    _call("ccd_mhsa_bwd", _p(qkv), _p(o), _p(_chk(d_o, torch.bfloat16)), _p(lse), _p(dqkv), S, H, _s(),
+    delta = torch.empty_like(lse)
+    _call("ccd_mhsa_bwd", _p(qkv), _p(o), _p(_chk(d_o, torch.bfloat16)), _p(lse), _p(delta), _p(dqkv), S, H, _s(),
           work=(10.0 * 256 * 256 * 64 * S * H, (S, H)))
     return dqkv
 

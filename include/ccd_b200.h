@@ -44,8 +44,10 @@ int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, int a_mn, i
  * variant 1: P staged through shared memory.  Replaces Attention.forward core, vision_transformer.py:85-89. */
 int ccd_mhsa_fwd(const void* qkv, void* out, float* lse2, int S, int H, int variant, void* stream);
 
-/* Fused MHSA backward: -> dqkv bf16 [S*256, 3*H*64].  Replaces autograd of vision_transformer.py:85-89. */
-int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int S, int H, void* stream);
+/* Fused MHSA backward: -> dqkv bf16 [S*256, 3*H*64]; delta_ws = f32 [S,H,256] workspace (rowsum(O*dO), written by a
+ * small pre-pass).  Replaces autograd of vision_transformer.py:85-89. */
+int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, float* delta_ws, void* dqkv, int S, int H,
+                 void* stream);
 
 /* LayerNorm (eps 1e-6) over f32 rows -> bf16 and/or f32.  Block.norm1/norm2, norm, norm_seg: vision_transformer.py:108-110,247,250 */
 int ccd_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, int rows, int E,
