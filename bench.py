@@ -43,6 +43,34 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (captured on this workload by tools/gpu_profile.sh); None if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_*.json")))
+    for path in reversed(files):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+        except Exception:
+            continue
+        vals = []
+        for rep in d.values():
+            for k in rep:
+                if kernel_substr in k.get("kernel", ""):
+                    def mb(s):
+                        v, u = s.split()[:2]
+                        return float(v) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
+                    try:
+                        vals.append(mb(k["dram__bytes_read.sum"]) + mb(k["dram__bytes_write.sum"]))
+                    except Exception:
+                        pass
+        if vals:
+            return {"avg_mbytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals), "source": os.path.basename(path),
+                    "note": "ncu --set full, captured launches of the dominant kernel within one step (mixed shapes)"}
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -302,9 +330,12 @@ def main():
         sh = d["shapes"].setdefault(str(work[1]), [0.0, 0.0, 0])
         sh[0] += dt; sh[1] += work[0]; sh[2] += 1
     gemm = agg.get("ccd_gemm_bf16", {"ms": 1e-9, "flops": 0.0, "n": 1})
+    traffic = ncu_traffic("gemm_umma_persistent_kernel")
     ach = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
     roofline = {"kernel": "gemm_umma_kernel (tcgen05 GEMM, all linear contractions fwd+bwd)", "bound": "tensor",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": (traffic["avg_mbytes_per_launch"] * 1e6 if traffic else None), "traffic_detail": traffic,
+                "algorithmic_flops_per_launch": gemm["flops"] / max(1, gemm["n"]),
                 "peak_source": peak_src, "launches": gemm["n"], "avg_launch_ms": gemm["ms"] / max(1, gemm["n"]),
                 "share_of_step": gemm["ms"] / ms,
                 "other": {k: {"ms_per_step": v["ms"] / K, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "launches": v["n"]}

@@ -176,3 +176,38 @@ def test_drop_path_and_epoch30_branch_run():
     loss30, _, so30, _, _, _ = run_step(student, teacher, 4096, 6, epoch=30)
     assert torch.isfinite(loss30)
     assert so30["instances_view"].shape[0] % 2 == 0
+
+
+def test_ragged_batch_with_empty_and_crowded_masks():
+    """Edge cases of the character path end to end (reference conventions): a batch size that is not a
+    multiple of anything, an EMPTY mask (-> clamp to 3 -> 4 all-zero rows that still go through the head), a mask with
+    more than 26 components (first 26 in label order), a mask whose components vanish under the warp.  Loss, cluster
+    maps, index and row count against the oracle."""
+    import ccd_oracle as O
+    from Dino.loss.Dino_loss import DINOLoss
+    from ccd_b200 import ops, synthetic as S
+    arch, E, K = "vit_tiny", 192, 2048
+    student, teacher, ssd, tsd = build(arch, E, K, 11, 12, 0.05, False)
+    B = 5
+    x, masks, metrics = S.make_batch(B, seed=77)
+    masks[1] = 0
+    masks[2] = 0
+    for c in range(40):
+        masks[2, 0:16, 3 * c: 3 * c + 2] = 1.0          # 40 components of 32 px
+    masks[3] = 0
+    masks[3, 0:8, 0:6] = 1.0                            # one component in the corner
+    metrics[3] = torch.tensor([[1.0, 0.0, 1.5], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])   # warped out of the image
+    x, masks, metrics = x.cuda(), masks.cuda(), metrics.cuda()
+    crit = DINOLoss(K, 2, 0.04, 0.04, 0, 101).cuda()
+    so = student(x, metrics, masks, 0, clusters=None)
+    to = teacher(x, metrics, None, None, clusters=so["zero"], index=so["index"])
+    so["gt"] = [masks, ops.warp_mask(masks, metrics)]
+    loss = crit(so, to, 0)
+    loss.backward()
+    L, parts = O.pretrain_loss(ssd, tsd, arch, x.cpu(), metrics.cpu(), masks.cpu(), torch.zeros(1, K), 0, 0.04)
+    assert torch.equal(so["zero"].dense().cpu(), parts["student"]["zero"])
+    assert torch.equal(so["index"].cpu(), parts["student"]["index"])
+    assert so["instances_view"].shape == parts["student"]["instances_view"].shape
+    assert abs(loss.item() - L.item()) / L.item() <= 1e-3
+    assert (so["instances_view"].detach().cpu() - parts["student"]["instances_view"].detach()).abs().max() <= 1e-2
+    assert all(torch.isfinite(p.grad).all() for p in student.parameters() if p.grad is not None)
