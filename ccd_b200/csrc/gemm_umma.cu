@@ -43,6 +43,21 @@ struct GemmParams {
                            // vision_transformer.py:27-36); null = 1
 };
 
+// Implicit-GEMM ("spatial") operand description for the SegHead convolutions (Dino/modules/segmentor.py:37-95): the
+// position dimension of an operand (M for a K-major A tile, K for an MN-major B tile) indexes an N x H x W grid of an
+// activation viewed as the 5-D tensor {C, W, P, H, N}; every tap adds an (dy, dx) shift (out-of-bounds = zero padding),
+// a parity plane P (transposed convolutions, stride 2) and a channel base.
+struct ConvSpec {
+  int a_spatial, b_spatial;
+  int H, W;                  // grid of the spatial operand's positions
+  int n_taps, cpt;           // taps; 64-channel chunks per tap (a_spatial: K = n_taps * cpt * 64)
+  int b_tap_cols;            // b_spatial: columns of N per tap (= cpt * 64)
+  signed char dy[16], dx[16], par[16];
+  short cbase[16];
+  int out_rowmap;            // epilogue: 1 = output row (n,a,b) -> (n, 2a+py, 2b+px) of an [N,2H,2W,*] tensor (ConvTranspose s2)
+  int py, px;
+};
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
@@ -326,10 +341,10 @@ __device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, i
   }
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, bool SPATIAL>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                            const GemmParams p_in, const PgWork wk) {
+                            const GemmParams p_in, const PgWork wk, const ConvSpec cs) {
   using Cfg = PgCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -386,7 +401,15 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           const int k0 = (kb_begin + i) * GEMM_BK;
           if (is_a) {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES);
-            if (!p_in.a_mn) {
+            if (SPATIAL && cs.a_spatial) {
+              // K-major A tile = 128 grid positions starting at m0, shifted by the tap of this k-block
+              const int kb = kb_begin + i;
+              const int tap = kb / cs.cpt, cc = kb - tap * cs.cpt;
+              const int hw = cs.H * cs.W;
+              const int n_img = m0 / hw, rem = m0 - n_img * hw;
+              const int y0 = rem / cs.W, x0 = rem - y0 * cs.W;
+              tma_load_5d(sa, &tmA, &full_bar[s], cs.cbase[tap] + cc * 64, x0 + cs.dx[tap], cs.par[tap], y0 + cs.dy[tap], n_img);
+            } else if (!p_in.a_mn) {
               tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
             } else {
               tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
@@ -394,7 +417,17 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES);
-            if (!p_in.b_mn) {
+            if (SPATIAL && cs.b_spatial) {
+              // MN-major B: 64 grid positions (k-block) x BN columns = (tap, channels) ; one box per 64 channels
+              const int tap = n0 / cs.b_tap_cols, c0 = n0 - tap * cs.b_tap_cols;
+              const int hw = cs.H * cs.W;
+              const int n_img = k0 / hw, rem = k0 - n_img * hw;
+              const int y0 = rem / cs.W, x0 = rem - y0 * cs.W;
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_5d(sb + j * 8192, &tmB, &full_bar[s], cs.cbase[tap] + c0 + 64 * j, x0 + cs.dx[tap], cs.par[tap],
+                            y0 + cs.dy[tap], n_img);
+            } else if (!p_in.b_mn) {
               tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
             } else {
 #pragma unroll
@@ -496,7 +529,14 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           if (col_ok && r < nrows) {
             float4 v = *reinterpret_cast<const float4*>(stage + r * 32 + ((sub_chunk ^ (r & 7)) * 4));
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            epilogue_row_aux<EPI>(p, row_base + r, col, v, ax[i]);
+            int orow = row_base + r;
+            if (SPATIAL && cs.out_rowmap) {      // ConvTranspose2d stride 2: scatter to the (py, px) parity positions
+              const int hw = cs.H * cs.W;
+              const int n_img = orow / hw, rem = orow - n_img * hw;
+              const int a = rem / cs.W, b = rem - a * cs.W;
+              orow = (n_img * 2 * cs.H + 2 * a + cs.py) * (2 * cs.W) + 2 * b + cs.px;
+            }
+            epilogue_row_aux<EPI>(p, orow, col, v, ax[i]);
           }
         }
         __syncwarp();                            // the 4 KB transpose buffer is rewritten by the next chunk
@@ -511,13 +551,13 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 
 static int g_gemm_variant = 1;   // 1 = persistent (default), 0 = one tile per CTA
 
-template <int EPI, int BN>
+template <int EPI, int BN, bool SPATIAL>
 static int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, const ConvSpec& cs) {
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
-    CCD_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<EPI, BN, SPATIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         PgCfg<BN>::SMEM));
     int dev = 0;
     CCD_CUDA_CHECK(cudaGetDevice(&dev));
@@ -529,7 +569,7 @@ static int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB
   wk.n_tiles = wk.n_tiles_n * ((p.M + GEMM_BM - 1) / GEMM_BM);
   wk.n_items = wk.n_tiles * splits;
   const int grid = wk.n_items < num_sms ? wk.n_items : num_sms;
-  gemm_umma_persistent_kernel<EPI, BN><<<grid, PG_THREADS, PgCfg<BN>::SMEM, stream>>>(tmA, tmB, p, wk);
+  gemm_umma_persistent_kernel<EPI, BN, SPATIAL><<<grid, PG_THREADS, PgCfg<BN>::SMEM, stream>>>(tmA, tmB, p, wk, cs);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }
@@ -546,9 +586,10 @@ static int dispatch_gemm_persistent(const void* A, const void* B, const GemmPara
   if (!p.b_mn) ok = get_tmap_bf16_2d(&tmB, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)bn, 64);
   else         ok = get_tmap_bf16_2d(&tmB, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.N, 64, 64);
   if (!ok) return CCD_ERR_TMAP;
-  if (bn == 256) return launch_gemm_persistent<EPI, 256>(tmA, tmB, p, splits, stream);
-  if (bn == 192) return launch_gemm_persistent<EPI, 192>(tmA, tmB, p, splits, stream);
-  return launch_gemm_persistent<EPI, 128>(tmA, tmB, p, splits, stream);
+  ConvSpec cs{};
+  if (bn == 256) return launch_gemm_persistent<EPI, 256, false>(tmA, tmB, p, splits, stream, cs);
+  if (bn == 192) return launch_gemm_persistent<EPI, 192, false>(tmA, tmB, p, splits, stream, cs);
+  return launch_gemm_persistent<EPI, 128, false>(tmA, tmB, p, splits, stream, cs);
 }
 
 template <int EPI, int BN>
@@ -621,6 +662,81 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
     case EPI_POS:   return launch_gemm<EPI_POS, BN>(tmA, tmB, p, splits, stream);
   }
   return CCD_ERR_ARG;
+}
+
+// Implicit-GEMM convolution entry (SegHead, Dino/modules/segmentor.py:37-95) on the persistent tcgen05 kernel.
+//   spatial_operand = 1: A is the activation (K-major, 128-position tiles): C[M=positions, N] = sum_taps A_shift(tap) * B
+//                        (conv3x3 / ConvTranspose forward and data gradients); B is a plain K-major [N, K] weight matrix.
+//   spatial_operand = 2: B is the activation (MN-major, K = positions): C[M, N=(tap, channel)] = A^T-style wgrad;
+//                        A is a plain MN-major [K=positions, M] matrix (the output gradient).
+// sp = the spatial activation, viewed as {C_total, W, P, H, n_img} (P = 2: row/column parity planes of an
+// [n_img, 2H, 2W, C_total/2] tensor).  taps_host = int[n_taps][4] = (dy, dx, parity_plane, channel_base).
+extern "C" int ccd_conv_gemm(const void* sp, const void* other, int M, int N, int K, int epi, const float* bias, void* out0,
+                             int ldc, int splits, int spatial_operand, int H, int W, int C_total, int P, int n_img, int n_taps,
+                             const int* taps_host, int cols_per_tap, int rowmap, int py, int px, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!sp || !other || !out0 || !taps_host || M <= 0 || N <= 0 || K <= 0 || (N & 7) || n_taps < 1 || n_taps > 16) return CCD_ERR_ARG;
+  if (epi != EPI_BF16 && epi != EPI_F32) return CCD_ERR_ARG;
+  if (spatial_operand != 1 && spatial_operand != 2) return CCD_ERR_ARG;
+  if (W > 128 && (W % 128)) return CCD_ERR_ARG;
+  if ((H * W) % 128 || (cols_per_tap % 64) || (C_total & 7)) return CCD_ERR_ARG;
+  if (ldc <= 0) ldc = N;
+  const int kb_total = (K + GEMM_BK - 1) / GEMM_BK;
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  if (splits > 1 && epi != EPI_F32) return CCD_ERR_ARG;
+  int kb_per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + kb_per - 1) / kb_per;
+
+  ConvSpec cs{};
+  cs.a_spatial = spatial_operand == 1;
+  cs.b_spatial = spatial_operand == 2;
+  cs.H = H; cs.W = W; cs.n_taps = n_taps;
+  cs.cpt = cols_per_tap / 64;
+  cs.b_tap_cols = cols_per_tap;
+  for (int t = 0; t < n_taps; ++t) {
+    cs.dy[t] = (signed char)taps_host[4 * t + 0];
+    cs.dx[t] = (signed char)taps_host[4 * t + 1];
+    cs.par[t] = (signed char)taps_host[4 * t + 2];
+    cs.cbase[t] = (short)taps_host[4 * t + 3];
+  }
+  cs.out_rowmap = rowmap; cs.py = py; cs.px = px;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.kb_per_split = kb_per;
+  p.bias = bias; p.out0 = out0; p.out1 = nullptr; p.aux = nullptr; p.ldc = ldc; p.atomic = (splits > 1) ? 1 : 0;
+  p.seq_scale = nullptr;
+
+  int bn;
+  CUtensorMap tmA, tmB;
+  const uint64_t dims[5] = {(uint64_t)C_total, (uint64_t)W, (uint64_t)P, (uint64_t)H, (uint64_t)n_img};
+  const uint64_t strides[4] = {(uint64_t)C_total, (uint64_t)W * C_total, (uint64_t)P * W * C_total, (uint64_t)H * P * W * C_total};
+  if (cs.a_spatial) {
+    if (K != n_taps * cols_per_tap || M != n_img * H * W) return CCD_ERR_ARG;
+    p.a_mn = 0; p.b_mn = 0;
+    bn = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : 128;
+    const uint32_t bw = W >= 128 ? 128 : (uint32_t)W;
+    if (!make_tmap_bf16_5d(&tmA, sp, dims, strides, bw, 128 / bw)) return CCD_ERR_TMAP;
+    if (!get_tmap_bf16_2d(&tmB, other, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, 64)) return CCD_ERR_TMAP;
+  } else {
+    if (N != n_taps * cols_per_tap || K != n_img * H * W) return CCD_ERR_ARG;
+    p.a_mn = 1; p.b_mn = 1;
+    // the N tile must not straddle two taps
+    bn = (cols_per_tap % 256 == 0) ? 256 : (cols_per_tap % 192 == 0) ? 192 : (cols_per_tap % 128 == 0) ? 128 : 0;
+    if (bn == 0) return CCD_ERR_ARG;
+    const uint32_t bw = W >= 64 ? 64 : (uint32_t)W;
+    if (!get_tmap_bf16_2d(&tmA, other, (uint64_t)K, (uint64_t)M, (uint64_t)M, 64, 64)) return CCD_ERR_TMAP;
+    if (!make_tmap_bf16_5d(&tmB, sp, dims, strides, bw, 64 / bw)) return CCD_ERR_TMAP;
+  }
+#define CCD_CONV_LAUNCH(E)                                                                    \
+  do {                                                                                        \
+    if (bn == 256) return launch_gemm_persistent<E, 256, true>(tmA, tmB, p, splits, stream, cs); \
+    if (bn == 192) return launch_gemm_persistent<E, 192, true>(tmA, tmB, p, splits, stream, cs); \
+    return launch_gemm_persistent<E, 128, true>(tmA, tmB, p, splits, stream, cs);               \
+  } while (0)
+  if (epi == EPI_BF16) CCD_CONV_LAUNCH(EPI_BF16);
+  CCD_CONV_LAUNCH(EPI_F32);
+#undef CCD_CONV_LAUNCH
 }
 
 // debug / A-B switch: key 0 = GEMM variant (1 persistent, 0 one-tile-per-CTA)

@@ -83,4 +83,24 @@ inline bool get_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, u
   return true;
 }
 
+// 5-D bf16 view {C (inner, contiguous), W, P, H, N} of an NHWC-like activation for implicit-GEMM convolutions:
+// strides in ELEMENTS for dims 1..4; box = {64 channels, box_w, 1, box_h, 1} (128B swizzle, zero fill out of bounds:
+// that is the convolution padding).  Not cached (cheap, a handful per step).
+inline bool make_tmap_bf16_5d(CUtensorMap* out, const void* ptr, const uint64_t dims[5], const uint64_t strides_elems[4],
+                              uint32_t box_w, uint32_t box_h) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  if ((uint64_t)ptr & 15) return false;
+  cuuint64_t gdim[5] = {dims[0], dims[1], dims[2], dims[3], dims[4]};
+  cuuint64_t gstride[4] = {strides_elems[0] * 2, strides_elems[1] * 2, strides_elems[2] * 2, strides_elems[3] * 2};
+  for (int i = 0; i < 4; ++i)
+    if (gstride[i] & 15) return false;
+  cuuint32_t box[5] = {64, box_w, 1, box_h, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace ccd

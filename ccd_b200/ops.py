@@ -393,3 +393,46 @@ def char_pool_bwd(drows, bits, tot4, cnt, offs, E):
     dtok = torch.empty(2 * n_view * 256, E, dtype=torch.float32, device=drows.device)
     _call("ccd_char_pool_bwd", _p(_chk(drows, torch.float32)), _p(bits), _p(tot4), _p(cnt), _p(offs), _p(dtok), n_view, E, _s())
     return dtok
+
+
+# ---- SegHead: implicit-GEMM convolutions + BatchNorm/ReLU ----
+def conv_gemm(sp, other, M, N, K, epi, bias, out0, ldc, splits, spatial_operand, H, W, C_total, P, n_img, taps, cols_per_tap,
+              rowmap=0, py=0, px=0):
+    """taps = list of (dy, dx, parity_plane, channel_base).  See include/ccd_b200.h:ccd_conv_gemm."""
+    arr = (ctypes.c_int * (4 * len(taps)))(*[int(v) for t in taps for v in t])
+    _call("ccd_conv_gemm", _p(sp), _p(other), M, N, K, epi, _p(bias), _p(out0), ldc, splits, spatial_operand, H, W, C_total, P,
+          n_img, len(taps), ctypes.cast(arr, ctypes.c_void_p), cols_per_tap, rowmap, py, px, _s(), work=(2.0 * M * N * K, ("conv", M, N, K)))
+    return out0
+
+
+def bn_stats(x, ldx, M, C):
+    sums = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+    _call("ccd_bn_stats", _p(x), ldx, _p(sums), M, C, _s())
+    return sums
+
+
+def bn_finalize(sums, count, eps, momentum, running_mean, running_var, C):
+    mean = torch.empty(C, dtype=torch.float32, device=sums.device)
+    rstd = torch.empty(C, dtype=torch.float32, device=sums.device)
+    _call("ccd_bn_finalize", _p(sums), float(count), float(eps), float(momentum), _p(mean), _p(rstd), _p(running_mean),
+          _p(running_var), C, _s())
+    return mean, rstd
+
+
+def bn_apply_relu(x, ldx, mean, rstd, gamma, beta, y, ldy, M, C):
+    _call("ccd_bn_apply_relu", _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(beta), _p(y), ldy, M, C, _s())
+    return y
+
+
+def bn_bwd_reduce(dy, lddy, x, ldx, mean, rstd, gamma, beta, M, C):
+    sums = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+    _call("ccd_bn_bwd_reduce", _p(dy), 1 if dy.dtype == torch.float32 else 0, lddy, _p(x), ldx, _p(mean), _p(rstd), _p(gamma),
+          _p(beta), _p(sums), M, C, _s())
+    return sums
+
+
+def bn_bwd_apply(dy, lddy, x, ldx, mean, rstd, gamma, beta, sums, inv_m, M, C):
+    dx = torch.empty(M, C, dtype=torch.bfloat16, device=x.device)
+    _call("ccd_bn_bwd_apply", _p(dy), 1 if dy.dtype == torch.float32 else 0, lddy, _p(x), ldx, _p(mean), _p(rstd), _p(gamma),
+          _p(beta), _p(sums), float(inv_m), _p(dx), C, M, C, _s())
+    return dx

@@ -1,13 +1,21 @@
-"""Segmentation head (drop-in for Dino/modules/segmentor.py:37-95, same parameter names / shapes).
+"""Segmentation head (drop-in for Dino/modules/segmentor.py:37-95, same parameter / buffer names and shapes) on the
+sm_100a kernels.
 
-ROUND-1 STATUS: the convolutions / transposed convolutions / BatchNorm of this head still run through PyTorch
-(cuDNN, channels-last, bf16 autocast for the convs) -- they are ~8 % of the step FLOPs and are the
-one part of the hot path that is NOT yet hand-written CUDA.  Its inputs (the three norm_seg taps) and its loss
-(ccd_seg_ce_fwd/bwd) are on the sm_100a kernels.  `conv_mla` is constructed but never called, exactly like the
-reference (its parameters never receive gradients: train.py:106 find_unused_parameters=True).
+  3 x [conv3x3 E->128 (no bias), BN, ReLU, conv1x1 128->64 (no bias), BN, ReLU] on the three norm_seg taps [N,E,8,32]
+  -> cat 192 -> ConvT 4x4 s2 (192->128) BN ReLU @16x64 -> ConvT 4x4 s2 (128->128) BN ReLU @32x128 -> conv3x3 128->2
+
+Every convolution is an implicit GEMM on the persistent tcgen05 kernel (`ccd_conv_gemm`): activations are NHWC bf16,
+the A (or, for weight gradients, B) operand is gathered by 5-D TMA boxes shifted per filter tap, zero fill = padding;
+the stride-2 transposed convolutions are four 2x2-tap GEMMs (one per output parity) whose epilogue scatters rows to the
+interleaved output, and their gradients gather the parity planes of the upsampled gradient through a {2*C, W, 2, H, N}
+view.  BatchNorm (training statistics, SyncBatchNorm when converted, train.py:96-98) + ReLU are row-streaming kernels.
+`conv_mla` is constructed but never called, exactly like the reference (its parameters never receive gradients).
 """
 import torch
+import torch.distributed as dist
 import torch.nn as nn
+
+from . import ops
 
 
 def _cbr(cin, cout, k, pad):
@@ -25,7 +33,7 @@ class Conv_MLA(nn.Module):          # segmentor.py:6-35 -- parameters only (unus
         self.mla_p4 = _cbr(mla_channels, mla_channels, 3, 1)
 
 
-class MLAHead(nn.Module):           # segmentor.py:37-70
+class MLAHead(nn.Module):           # segmentor.py:37-70 (parameter container; SegHead.forward drives the kernels)
     def __init__(self, in_channels=384, mla_channels=128, mlahead_channels=64):
         super().__init__()
 
@@ -35,26 +43,234 @@ class MLAHead(nn.Module):           # segmentor.py:37-70
                                  nn.BatchNorm2d(mlahead_channels), nn.ReLU())
         self.head2, self.head3, self.head4 = branch(), branch(), branch()
 
-    def forward(self, p2, p3, p4):
-        return torch.cat([self.head2(p2), self.head3(p3), self.head4(p4)], dim=1)
+
+# filter taps ------------------------------------------------------------------------------------------------
+CONV3_FWD_TAPS = [(ky - 1, kx - 1, 0, 0) for ky in range(3) for kx in range(3)]          # input pixel (y+ky-1, x+kx-1)
+CONV3_DGRAD_TAPS = [(1 - ky, 1 - kx, 0, 0) for ky in range(3) for kx in range(3)]        # dY pixel (y-(ky-1), x-(kx-1))
+# ConvTranspose2d(k=4, s=2, p=1): out[2a+py] gets in[a + d] * W[ky] for (d, ky) in
+_CT_FWD = {0: ((0, 1), (-1, 3)), 1: ((0, 2), (1, 0))}
+# its data gradient: in[a] gets dOut[2(a+d)+p] * W[ky] for ky -> (d, p)
+_CT_BWD = {0: (-1, 1), 1: (0, 0), 2: (0, 1), 3: (1, 0)}
+
+
+def convt_fwd_taps(py, px):
+    """-> (taps, [(ky, kx)]) of the 2x2 sub-filter producing output parity (py, px)."""
+    taps, kk = [], []
+    for dy, ky in _CT_FWD[py]:
+        for dx, kx in _CT_FWD[px]:
+            taps.append((dy, dx, 0, 0))
+            kk.append((ky, kx))
+    return taps, kk
+
+
+def convt_bwd_taps(cout):
+    """16 taps over the {2*cout, W, 2, H, N} parity view of the upsampled gradient; tap index = ky*4 + kx."""
+    taps = []
+    for ky in range(4):
+        for kx in range(4):
+            dy, py = _CT_BWD[ky]
+            dx, px = _CT_BWD[kx]
+            taps.append((dy, dx, py, px * cout))
+    return taps
 
 
 class SegHead(nn.Module):           # segmentor.py:73-95
     def __init__(self, in_channels=384, mla_channels=128, mlahead_channels=64, num_classes=2, **kwargs):
         super().__init__()
+        if mla_channels != 128 or mlahead_channels != 64 or num_classes != 2 or in_channels % 64:
+            raise NotImplementedError("ccd_b200.SegHead implements the CCD configuration (128 / 64 channels, 2 classes)")
         self.num_classes = num_classes
+        self.in_channels = in_channels
         self.conv_mla = Conv_MLA(in_channels, mla_channels)
         self.mlahead = MLAHead(in_channels=in_channels, mla_channels=mla_channels, mlahead_channels=mlahead_channels)
         self.unpool1 = nn.Sequential(nn.ConvTranspose2d(192, 128, (4, 4), (2, 2), (1, 1)), nn.BatchNorm2d(128), nn.ReLU(True))
         self.unpool2 = nn.Sequential(nn.ConvTranspose2d(128, 128, (4, 4), (2, 2), (1, 1)), nn.BatchNorm2d(128), nn.ReLU(True))
         self.cls = nn.Conv2d(128, self.num_classes, 3, padding=1)
-        self.autocast_bf16 = True
+
+    def _bn_layers(self):
+        h = self.mlahead
+        return [h.head2[1], h.head2[4], h.head3[1], h.head3[4], h.head4[1], h.head4[4], self.unpool1[1], self.unpool2[1]]
 
     def forward(self, inputs):
-        dev = inputs[0].device.type
-        with torch.autocast(device_type=dev, dtype=torch.bfloat16, enabled=self.autocast_bf16 and dev == "cuda"):
-            x = self.mlahead(inputs[0], inputs[1], inputs[2])
-            x = self.unpool1(x)
-            x = self.unpool2(x)
-            x = self.cls(x)
-        return x.float()
+        if not inputs[0].is_cuda:
+            raise RuntimeError("ccd_b200.SegHead runs on CUDA (sm_100a) only; there is no CPU path")
+        h = self.mlahead
+        params = []
+        for br in (h.head2, h.head3, h.head4):
+            params += [br[0].weight, br[1].weight, br[1].bias, br[3].weight, br[4].weight, br[4].bias]
+        params += [self.unpool1[0].weight, self.unpool1[0].bias, self.unpool1[1].weight, self.unpool1[1].bias,
+                   self.unpool2[0].weight, self.unpool2[0].bias, self.unpool2[1].weight, self.unpool2[1].bias,
+                   self.cls.weight, self.cls.bias]
+        # taps arrive as [N,E,8,32] views of NHWC storage (encoder.VisionTransformer.forward): recover [N*256, E]
+        taps = [t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]) for t in inputs]
+        return SegHeadFn.apply(self, *taps, *params)
+
+
+def _bn_forward(bn, z, ldz, M, C, y, ldy, training):
+    """BatchNorm2d / SyncBatchNorm (training: batch statistics, running-stat update) + ReLU.  Returns (mean, rstd, count)."""
+    if training:
+        sums = ops.bn_stats(z, ldz, M, C)
+        count = float(M)
+        if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(sums)
+            count *= dist.get_world_size()
+        mom = 0.1 if bn.momentum is None else bn.momentum
+        mean, rstd = ops.bn_finalize(sums, count, bn.eps, mom, bn.running_mean if bn.track_running_stats else None,
+                                     bn.running_var if bn.track_running_stats else None, C)
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+    else:
+        mean = bn.running_mean.float()
+        rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+        count = float(M)
+    ops.bn_apply_relu(z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), y, ldy, M, C)
+    return mean, rstd, count
+
+
+def _bn_backward(bn, dy, lddy, z, ldz, mean, rstd, count, M, C):
+    """-> (dz bf16 [M,C], dgamma, dbeta)."""
+    sums = ops.bn_bwd_reduce(dy, lddy, z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), M, C)
+    dbeta, dgamma = sums[:C].clone(), sums[C:].clone()          # local sums = parameter gradients (DDP averages them)
+    if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(sums)
+    dz = ops.bn_bwd_apply(dy, lddy, z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), sums, 1.0 / count, M, C)
+    return dz, dgamma, dbeta
+
+
+class SegHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, t0, t1, t2, *params):
+        dev = t0.device
+        E = mod.in_channels
+        T = t0.shape[0]
+        n = T // 256
+        M1, M2 = n * 1024, n * 4096
+        b16 = dict(dtype=torch.bfloat16, device=dev)
+        training = mod.training
+        h = mod.mlahead
+        branches = (h.head2, h.head3, h.head4)
+        saved = {"n": n, "bn": []}
+        cat = torch.empty(T, 192, **b16)
+        xs, zas, acts, zbs = [], [], [], []
+        for i, (br, tap) in enumerate(zip(branches, (t0, t1, t2))):
+            w0, w3 = params[6 * i].detach(), params[6 * i + 3].detach()
+            x = ops.cast_bf16(tap.contiguous().float()) if tap.dtype != torch.bfloat16 else tap.contiguous()
+            wf = w0.permute(0, 2, 3, 1).reshape(128, 9 * E).to(torch.bfloat16).contiguous()         # [o][tap][c]
+            za = torch.empty(T, 128, **b16)
+            ops.conv_gemm(x, wf, T, 128, 9 * E, ops.EPI_BF16, None, za, 128, 1, 1, 8, 32, E, 1, n, CONV3_FWD_TAPS, E)
+            a = torch.empty(T, 128, **b16)
+            st_a = _bn_forward(br[1], za, 128, T, 128, a, 128, training)
+            zb = torch.empty(T, 64, **b16)
+            ops.linear_fwd(a, w3.reshape(64, 128).to(torch.bfloat16).contiguous(), None, ops.EPI_BF16, zb)
+            st_b = _bn_forward(br[4], zb, 64, T, 64, cat[:, 64 * i:], 192, training)
+            xs.append(x); zas.append(za); acts.append(a); zbs.append(zb)
+            saved["bn"] += [st_a, st_b]
+        # unpool1: ConvTranspose2d(192 -> 128) 8x32 -> 16x64, four parity GEMMs
+        wu1, bu1 = params[18].detach(), params[19].detach()
+        zu1 = torch.empty(M1, 128, **b16)
+        for py in range(2):
+            for px in range(2):
+                taps, kk = convt_fwd_taps(py, px)
+                wpar = torch.stack([wu1[:, :, ky, kx] for ky, kx in kk], 0).permute(2, 0, 1).reshape(128, 4 * 192)
+                ops.conv_gemm(cat, wpar.to(torch.bfloat16).contiguous(), T, 128, 4 * 192, ops.EPI_BF16, bu1.float(), zu1, 128, 1, 1,
+                              8, 32, 192, 1, n, taps, 192, rowmap=1, py=py, px=px)
+        u1 = torch.empty(M1, 128, **b16)
+        st_u1 = _bn_forward(mod.unpool1[1], zu1, 128, M1, 128, u1, 128, training)
+        # unpool2: ConvTranspose2d(128 -> 128) 16x64 -> 32x128
+        wu2, bu2 = params[22].detach(), params[23].detach()
+        zu2 = torch.empty(M2, 128, **b16)
+        for py in range(2):
+            for px in range(2):
+                taps, kk = convt_fwd_taps(py, px)
+                wpar = torch.stack([wu2[:, :, ky, kx] for ky, kx in kk], 0).permute(2, 0, 1).reshape(128, 4 * 128)
+                ops.conv_gemm(u1, wpar.to(torch.bfloat16).contiguous(), M1, 128, 4 * 128, ops.EPI_BF16, bu2.float(), zu2, 128, 1, 1,
+                              16, 64, 128, 1, n, taps, 128, rowmap=1, py=py, px=px)
+        u2 = torch.empty(M2, 128, **b16)
+        st_u2 = _bn_forward(mod.unpool2[1], zu2, 128, M2, 128, u2, 128, training)
+        # cls: conv3x3 128 -> 2 (outputs padded to 8 columns)
+        wc, bc = params[26].detach(), params[27].detach()
+        wcf = torch.zeros(8, 9 * 128, **b16)
+        wcf[:2] = wc.permute(0, 2, 3, 1).reshape(2, 9 * 128)
+        bc8 = torch.zeros(8, dtype=torch.float32, device=dev)
+        bc8[:2] = bc
+        out8 = torch.empty(M2, 8, dtype=torch.float32, device=dev)
+        ops.conv_gemm(u2, wcf, M2, 8, 9 * 128, ops.EPI_F32, bc8, out8, 8, 1, 1, 32, 128, 128, 1, n, CONV3_FWD_TAPS, 128)
+        logits = out8[:, :2].reshape(n, 32, 128, 2).permute(0, 3, 1, 2).contiguous()
+        if any(ctx.needs_input_grad):
+            saved["bn"] += [st_u1, st_u2]
+            ctx.mod, ctx.E, ctx.params = mod, E, params
+            ctx.saved = (saved, xs, zas, acts, zbs, cat, zu1, u1, zu2, u2)
+        return logits
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        mod, E, params = ctx.mod, ctx.E, ctx.params
+        saved, xs, zas, acts, zbs, cat, zu1, u1, zu2, u2 = ctx.saved
+        n = saved["n"]
+        T, M1, M2 = n * 256, n * 1024, n * 4096
+        dev = cat.device
+        b16 = dict(dtype=torch.bfloat16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        h = mod.mlahead
+        branches = (h.head2, h.head3, h.head4)
+        grads = [None] * len(params)
+        st = saved["bn"]
+        # ---- cls ----
+        d8 = torch.zeros(M2, 8, **b16)
+        d8[:, :2] = d_logits.permute(0, 2, 3, 1).reshape(M2, 2)
+        wc = params[26].detach()
+        gb = torch.zeros(8, **f32)
+        ops.colsum_bf16(d8, gb)
+        grads[27] = gb[:2].clone()
+        gw = torch.zeros(8, 9 * 128, **f32)
+        ops.conv_gemm(u2, d8, 8, 9 * 128, M2, ops.EPI_F32, None, gw, 9 * 128, ops.wgrad_splits(128, 9 * 128, M2), 2, 32, 128, 128, 1, n,
+                      CONV3_FWD_TAPS, 128)
+        grads[26] = gw[:2].reshape(2, 3, 3, 128).permute(0, 3, 1, 2).contiguous()
+        wd = torch.zeros(128, 9, 64, **b16)                                     # [c][tap][o padded to 64]
+        wd[:, :, :2] = wc.permute(1, 2, 3, 0).reshape(128, 9, 2)
+        du2 = torch.empty(M2, 128, **b16)
+        ops.conv_gemm(d8, wd.reshape(128, 9 * 64), M2, 128, 9 * 64, ops.EPI_BF16, None, du2, 128, 1, 1, 32, 128, 8, 1, n,
+                      CONV3_DGRAD_TAPS, 64)
+        # ---- unpool2 ----
+        dz2, grads[24], grads[25] = _bn_backward(mod.unpool2[1], du2, 128, zu2, 128, *st[7], M2, 128)
+        grads[23] = ops.colsum_bf16(dz2, torch.zeros(128, **f32))
+        wu2 = params[22].detach()
+        tb = convt_bwd_taps(128)
+        gw2 = torch.zeros(128, 16 * 128, **f32)                                  # [cin][tap][o]
+        ops.conv_gemm(dz2, u1, 128, 16 * 128, M1, ops.EPI_F32, None, gw2, 16 * 128, ops.wgrad_splits(128, 16 * 128, M1), 2, 16, 64, 256, 2,
+                      n, tb, 128)
+        grads[22] = gw2.reshape(128, 4, 4, 128).permute(0, 3, 1, 2).contiguous()
+        wd2 = wu2.permute(0, 2, 3, 1).reshape(128, 16 * 128).to(torch.bfloat16).contiguous()      # [cin][tap][o]
+        du1 = torch.empty(M1, 128, **b16)
+        ops.conv_gemm(dz2, wd2, M1, 128, 16 * 128, ops.EPI_BF16, None, du1, 128, 1, 1, 16, 64, 256, 2, n, tb, 128)
+        # ---- unpool1 ----
+        dz1, grads[20], grads[21] = _bn_backward(mod.unpool1[1], du1, 128, zu1, 128, *st[6], M1, 128)
+        grads[19] = ops.colsum_bf16(dz1, torch.zeros(128, **f32))
+        wu1 = params[18].detach()
+        gw1 = torch.zeros(192, 16 * 128, **f32)
+        ops.conv_gemm(dz1, cat, 192, 16 * 128, T, ops.EPI_F32, None, gw1, 16 * 128, ops.wgrad_splits(192, 16 * 128, T), 2, 8, 32, 256, 2, n,
+                      tb, 128)
+        grads[18] = gw1.reshape(192, 4, 4, 128).permute(0, 3, 1, 2).contiguous()
+        wd1 = wu1.permute(0, 2, 3, 1).reshape(192, 16 * 128).to(torch.bfloat16).contiguous()
+        dcat = torch.empty(T, 192, **b16)
+        ops.conv_gemm(dz1, wd1, T, 192, 16 * 128, ops.EPI_BF16, None, dcat, 192, 1, 1, 8, 32, 256, 2, n, tb, 128)
+        # ---- the three branches ----
+        d_taps = []
+        for i, br in enumerate(branches):
+            w0, w3 = params[6 * i].detach(), params[6 * i + 3].detach()
+            dzb, grads[6 * i + 4], grads[6 * i + 5] = _bn_backward(br[4], dcat[:, 64 * i:], 192, zbs[i], 64, *st[2 * i + 1], T, 64)
+            gw3 = torch.zeros(64, 128, **f32)
+            ops.linear_wgrad(dzb, acts[i], gw3)
+            grads[6 * i + 3] = gw3.reshape(64, 128, 1, 1)
+            da = torch.empty(T, 128, **b16)
+            ops.linear_dgrad(dzb, w3.reshape(64, 128).to(torch.bfloat16).contiguous(), ops.EPI_BF16, da)
+            dza, grads[6 * i + 1], grads[6 * i + 2] = _bn_backward(br[1], da, 128, zas[i], 128, *st[2 * i], T, 128)
+            gw0 = torch.zeros(128, 9 * E, **f32)
+            ops.conv_gemm(xs[i], dza, 128, 9 * E, T, ops.EPI_F32, None, gw0, 9 * E, ops.wgrad_splits(128, 9 * E, T), 2, 8, 32, E, 1, n,
+                          CONV3_FWD_TAPS, E)
+            grads[6 * i] = gw0.reshape(128, 3, 3, E).permute(0, 3, 1, 2).contiguous()
+            wd0 = w0.permute(1, 2, 3, 0).reshape(E, 9 * 128).to(torch.bfloat16).contiguous()      # [c][tap][o]
+            dt = torch.empty(T, E, **f32)
+            ops.conv_gemm(dza, wd0, T, E, 9 * 128, ops.EPI_F32, None, dt, E, 1, 1, 8, 32, 128, 1, n, CONV3_DGRAD_TAPS, 128)
+            d_taps.append(dt)
+        return (None, *d_taps, *grads)

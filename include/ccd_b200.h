@@ -109,6 +109,30 @@ int ccd_char_pool_fwd(const void* tokens, int tokens_bf16, const void* bits, con
 int ccd_char_pool_bwd(const float* drows, const void* bits, const int* tot4, const int* cnt, const int* offs, float* dtokens,
                       int n_view, int E, void* stream);
 
+/* ---- SegHead (Dino/modules/segmentor.py:37-95): implicit-GEMM convolutions + BatchNorm(train)+ReLU, NHWC bf16 ----
+ * ccd_conv_gemm: the persistent tcgen05 GEMM with one operand gathered from an activation {C_total, W, P, H, n_img} through
+ * 5-D TMA boxes shifted per tap (zero fill = padding).  spatial_operand 1: C[M=positions, N] = sum_taps shift_tap(sp) * other[N, K]^T
+ * (conv3x3 / ConvTranspose2d forward and dgrad; rowmap=1 scatters rows to the (py,px) parity positions of a 2x upsampled output);
+ * spatial_operand 2: C[M, N=(tap, channel)] = other[K=positions, M]^T * shift_tap(sp)  (weight gradients, split-K).
+ * taps_host = host int[n_taps][4] = (dy, dx, parity plane, channel base); epi = CCD_EPI_BF16 | CCD_EPI_F32. */
+int ccd_conv_gemm(const void* sp, const void* other, int M, int N, int K, int epi, const float* bias, void* out0, int ldc,
+                  int splits, int spatial_operand, int H, int W, int C_total, int P, int n_img, int n_taps, const int* taps_host,
+                  int cols_per_tap, int rowmap, int py, int px, void* stream);
+/* BatchNorm2d training statistics: sums[0:C] += sum x, sums[C:2C] += sum x^2 over the M rows of x bf16 [M, C] (ld ldx) */
+int ccd_bn_stats(const void* x, int ldx, float* sums_zeroed, int M, int C, void* stream);
+/* mean/rstd from the (all-reduced) sums over `count` rows; running_mean/var (nullable) updated with `momentum` */
+int ccd_bn_finalize(const float* sums, float count, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                    float* running_var, int C, void* stream);
+/* y = relu((x - mean) * rstd * gamma + beta)  -> bf16 [M, C] with leading dimension ldy (torch.cat fused through ldy) */
+int ccd_bn_apply_relu(const void* x, int ldx, const float* mean, const float* rstd, const float* gamma, const float* beta, void* y,
+                      int ldy, int M, int C, void* stream);
+/* BN+ReLU backward pass 1: sums[0:C] += sum dz, sums[C:2C] += sum dz*xhat, dz = dy * [y > 0]; pass 2: dx bf16 */
+int ccd_bn_bwd_reduce(const void* dy, int dy_is_f32, int lddy, const void* x, int ldx, const float* mean, const float* rstd,
+                      const float* gamma, const float* beta, float* sums_zeroed, int M, int C, void* stream);
+int ccd_bn_bwd_apply(const void* dy, int dy_is_f32, int lddy, const void* x, int ldx, const float* mean, const float* rstd,
+                     const float* gamma, const float* beta, const float* sums, float inv_m, void* dx, int lddx, int M, int C,
+                     void* stream);
+
 /* debug / A-B switches (process-global): key 0 = GEMM variant (1 = persistent [default], 0 = one tile per CTA) */
 int ccd_set_option(int key, int value);
 
