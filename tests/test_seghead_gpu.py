@@ -145,8 +145,8 @@ def test_seghead_against_oracle(E):
             assert p.grad is None
             continue
         r = osd["segmentation." + k].grad
-        if r.norm() < 1e-6:
-            continue                                   # conv biases in front of a BatchNorm: gradient is pure rounding noise
+        if r.norm() < 1e-6 or k in ("unpool1.0.bias", "unpool2.0.bias"):
+            continue        # a bias in front of a training-mode BatchNorm has zero gradient: both sides are rounding noise
         if cos(p.grad, r) < 0.985:
             bad.append((k, cos(p.grad, r)))
     assert not bad, bad
