@@ -167,6 +167,145 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// cls: Conv2d(128 -> 2, 3x3, pad 1) on the [n,32,128,128] bf16 feature map (segmentor.py:88,94).  Two output channels
+// cannot feed a tensor-core tile (a 128-wide UMMA tile would waste 98 % of its MACs), so forward, data gradient and
+// weight gradient are CUDA-core kernels: one CTA per image row with the three input rows staged in shared memory
+// (pixel pitch 272 B = 256 B + 16 B pad: the per-pixel channel vectors of neighbouring pixels start in different banks).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CLS_W = 128, CLS_H = 32, CLS_C = 128;
+constexpr int CLS_PITCH = 272;                          // bytes per pixel in smem
+constexpr int CLS_ROW_BYTES = (CLS_W + 2) * CLS_PITCH;  // zero pixel on each side
+constexpr int CLS_ROWS_BYTES = 3 * CLS_ROW_BYTES;       // 106080
+constexpr int CLS_WS = CLS_C + 4;
+
+// stage rows y-1, y, y+1 of image n (zeros outside the image) ; all threads of the CTA participate
+__device__ __forceinline__ void cls_stage_rows(uint8_t* rows, const bf16* __restrict__ u2, int n, int y) {
+  for (int i = threadIdx.x; i < 3 * 2 * (CLS_PITCH / 16); i += blockDim.x) {        // left / right border pixels
+    const int r = i / (2 * (CLS_PITCH / 16)), rem = i % (2 * (CLS_PITCH / 16));
+    const int side = rem / (CLS_PITCH / 16), ch = rem % (CLS_PITCH / 16);
+    *reinterpret_cast<uint4*>(rows + r * CLS_ROW_BYTES + (side ? (CLS_W + 1) : 0) * CLS_PITCH + ch * 16) = make_uint4(0, 0, 0, 0);
+  }
+  for (int i = threadIdx.x; i < 3 * CLS_W * 16; i += blockDim.x) {
+    const int r = i / (CLS_W * 16), rem = i % (CLS_W * 16);
+    const int px = rem >> 4, ch = rem & 15;
+    const int yy = y + r - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < CLS_H) v = *reinterpret_cast<const uint4*>(u2 + (((size_t)n * CLS_H + yy) * CLS_W + px) * CLS_C + ch * 8);
+    *reinterpret_cast<uint4*>(rows + r * CLS_ROW_BYTES + (px + 1) * CLS_PITCH + ch * 16) = v;
+  }
+}
+
+// logits[n,o,y,x] = bias[o] + sum_{ky,kx,c} u2[n, y+ky-1, x+kx-1, c] * w[o,c,ky,kx]        (NCHW fp32 output)
+__global__ void __launch_bounds__(256) seg_cls_fwd_kernel(const bf16* __restrict__ u2, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ logits) {
+  extern __shared__ __align__(16) uint8_t cls_smem[];
+  uint8_t* rows = cls_smem;
+  float* wsm = reinterpret_cast<float*>(cls_smem + CLS_ROWS_BYTES);      // [tap][o][c], class stride 132 floats (banks)
+  const int n = blockIdx.x / CLS_H, y = blockIdx.x % CLS_H;
+  for (int i = threadIdx.x; i < 9 * 2 * CLS_C; i += blockDim.x) {
+    const int tap = i / (2 * CLS_C), o = (i / CLS_C) & 1, c = i % CLS_C;
+    wsm[(tap * 2 + o) * CLS_WS + c] = w[(o * CLS_C + c) * 9 + tap];
+  }
+  cls_stage_rows(rows, u2, n, y);
+  __syncthreads();
+  const int x = threadIdx.x >> 1, o = threadIdx.x & 1;
+  float acc = bias[o];
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    const uint8_t* px = rows + ky * CLS_ROW_BYTES + (x + kx) * CLS_PITCH;      // (x + kx - 1) + 1 border
+    const float* wt = wsm + (tap * 2 + o) * CLS_WS;
+#pragma unroll
+    for (int cq = 0; cq < 16; ++cq) {
+      const uint4 v = *reinterpret_cast<const uint4*>(px + cq * 16);
+      const float4 w0 = *reinterpret_cast<const float4*>(wt + cq * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wt + cq * 8 + 4);
+      acc += bf16lo(v.x) * w0.x + bf16hi(v.x) * w0.y + bf16lo(v.y) * w0.z + bf16hi(v.y) * w0.w + bf16lo(v.z) * w1.x +
+             bf16hi(v.z) * w1.y + bf16lo(v.w) * w1.z + bf16hi(v.w) * w1.w;
+    }
+  }
+  logits[(((size_t)n * 2 + o) * CLS_H + y) * CLS_W + x] = acc;
+}
+
+// du2[n,y,x,c] = sum_{ky,kx,o} dl[n,o, y-(ky-1), x-(kx-1)] * w[o,c,ky,kx]       (dl NCHW fp32, du2 NHWC bf16)
+__global__ void __launch_bounds__(256) seg_cls_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w,
+                                                            bf16* __restrict__ du2) {
+  __shared__ float dls[3][2][CLS_W + 2];
+  const int n = blockIdx.x / CLS_H, y = blockIdx.x % CLS_H;
+  for (int i = threadIdx.x; i < 3 * 2 * (CLS_W + 2); i += blockDim.x) {
+    const int r = i / (2 * (CLS_W + 2)), o = (i / (CLS_W + 2)) & 1, xx = i % (CLS_W + 2) - 1;
+    const int yy = y + r - 1;
+    dls[r][o][xx + 1] = (yy >= 0 && yy < CLS_H && xx >= 0 && xx < CLS_W) ? dl[(((size_t)n * 2 + o) * CLS_H + yy) * CLS_W + xx] : 0.f;
+  }
+  // this thread's 4 channels of every tap / class: 72 weights in registers
+  const int cg = threadIdx.x & 31, pl = threadIdx.x >> 5;          // channel group (4 ch), pixel lane (8 pixels per pass)
+  float wr[9][2][4];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wr[tap][o][j] = w[(o * CLS_C + cg * 4 + j) * 9 + tap];
+  __syncthreads();
+#pragma unroll 1
+  for (int x = pl; x < CLS_W; x += 8) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      const float d0 = dls[2 - ky][0][x + 2 - kx], d1 = dls[2 - ky][1][x + 2 - kx];     // row y+1-ky, col x+1-kx (+1 border)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] = fmaf(d0, wr[tap][0][j], fmaf(d1, wr[tap][1][j], a[j]));
+    }
+    *reinterpret_cast<uint2*>(du2 + (((size_t)n * CLS_H + y) * CLS_W + x) * CLS_C + cg * 4) =
+        make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
+  }
+}
+
+// dw[o,c,ky,kx] += sum_{n,y,x} dl[n,o,y,x] * u2[n, y+ky-1, x+kx-1, c]   ; persistent CTAs over image rows, dw zero-filled
+__global__ void __launch_bounds__(256) seg_cls_wgrad_kernel(const bf16* __restrict__ u2, const float* __restrict__ dl,
+                                                            float* __restrict__ dw, float* __restrict__ dbias, int n_rows_total) {
+  extern __shared__ __align__(16) uint8_t cls_smem[];
+  uint8_t* rows = cls_smem;
+  float* dls = reinterpret_cast<float*>(cls_smem + CLS_ROWS_BYTES);      // [2][128]
+  const int cp = threadIdx.x & 63, xq = threadIdx.x >> 6;                 // channel pair, pixel quarter
+  float acc[9][2][2];                                                      // [tap][channel of the pair][class]
+#pragma unroll
+  for (int t = 0; t < 9; ++t) { acc[t][0][0] = acc[t][0][1] = acc[t][1][0] = acc[t][1][1] = 0.f; }
+  float bs0 = 0.f, bs1 = 0.f;                                              // cls.bias gradient (threads with cp == 0)
+  for (int row = blockIdx.x; row < n_rows_total; row += gridDim.x) {
+    const int n = row / CLS_H, y = row % CLS_H;
+    __syncthreads();                                                       // previous row fully consumed
+    cls_stage_rows(rows, u2, n, y);
+    for (int i = threadIdx.x; i < 2 * CLS_W; i += blockDim.x)
+      dls[i] = dl[(((size_t)n * 2 + (i >> 7)) * CLS_H + y) * CLS_W + (i & 127)];
+    __syncthreads();
+#pragma unroll 1
+    for (int x = xq * 32; x < xq * 32 + 32; ++x) {
+      const float d0 = dls[x], d1 = dls[CLS_W + x];
+      bs0 += d0; bs1 += d1;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(rows + ky * CLS_ROW_BYTES + (x + kx) * CLS_PITCH + cp * 4);
+        const float c0 = bf16lo(v), c1 = bf16hi(v);
+        acc[tap][0][0] = fmaf(d0, c0, acc[tap][0][0]); acc[tap][0][1] = fmaf(d1, c0, acc[tap][0][1]);
+        acc[tap][1][0] = fmaf(d0, c1, acc[tap][1][0]); acc[tap][1][1] = fmaf(d1, c1, acc[tap][1][1]);
+      }
+    }
+  }
+  // four pixel quarters hold partial sums of the same (o, c, tap): atomics into global (296 CTAs x 2304 addresses)
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int o = 0; o < 2; ++o) atomicAdd(dw + (o * CLS_C + cp * 2 + j) * 9 + tap, acc[tap][j][o]);
+  if (cp == 0) { atomicAdd(dbias, bs0); atomicAdd(dbias + 1, bs1); }
+}
+
 }  // namespace ccd
 
 using namespace ccd;
@@ -228,6 +367,41 @@ extern "C" int ccd_bn_finalize(const float* sums, float count, float eps, float 
                                float* running_mean, float* running_var, int C, void* stream) {
   if (!sums || !mean || !rstd || C <= 0 || count <= 0.f) return CCD_ERR_ARG;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, eps, momentum, mean, rstd, running_mean, running_var, C);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_seg_cls_fwd(const void* u2, const float* w, const float* bias, float* logits, int n_img, void* stream) {
+  if (!u2 || !w || !bias || !logits || n_img <= 0) return CCD_ERR_ARG;
+  const int smem = CLS_ROWS_BYTES + 9 * 2 * CLS_WS * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(seg_cls_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  seg_cls_fwd_kernel<<<n_img * CLS_H, 256, smem, (cudaStream_t)stream>>>((const bf16*)u2, w, bias, logits);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_seg_cls_dgrad(const float* dl, const float* w, void* du2, int n_img, void* stream) {
+  if (!dl || !w || !du2 || n_img <= 0) return CCD_ERR_ARG;
+  seg_cls_dgrad_kernel<<<n_img * CLS_H, 256, 0, (cudaStream_t)stream>>>(dl, w, (bf16*)du2);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_seg_cls_wgrad(const void* u2, const float* dl, float* dw_zeroed, float* dbias_zeroed, int n_img, void* stream) {
+  if (!u2 || !dl || !dw_zeroed || !dbias_zeroed || n_img <= 0) return CCD_ERR_ARG;
+  const int smem = CLS_ROWS_BYTES + 2 * CLS_W * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(seg_cls_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int rows = n_img * CLS_H;
+  const int grid = rows < 296 ? rows : 296;
+  seg_cls_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)u2, dl, dw_zeroed, dbias_zeroed, rows);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }

@@ -436,3 +436,21 @@ def bn_bwd_apply(dy, lddy, x, ldx, mean, rstd, gamma, beta, sums, inv_m, M, C):
     _call("ccd_bn_bwd_apply", _p(dy), 1 if dy.dtype == torch.float32 else 0, lddy, _p(x), ldx, _p(mean), _p(rstd), _p(gamma),
           _p(beta), _p(sums), float(inv_m), _p(dx), C, M, C, _s())
     return dx
+
+
+def seg_cls_fwd(u2, w, bias, n_img):
+    logits = torch.empty(n_img, 2, 32, 128, dtype=torch.float32, device=u2.device)
+    _call("ccd_seg_cls_fwd", _p(u2), _p(_chk(w, torch.float32)), _p(bias), _p(logits), n_img, _s())
+    return logits
+
+
+def seg_cls_dgrad(dl, w, n_img):
+    du2 = torch.empty(n_img * 4096, 128, dtype=torch.bfloat16, device=dl.device)
+    _call("ccd_seg_cls_dgrad", _p(_chk(dl, torch.float32)), _p(_chk(w, torch.float32)), _p(du2), n_img, _s())
+    return du2
+
+
+def seg_cls_wgrad(u2, dl, n_img):
+    buf = torch.zeros(2 * 128 * 9 + 2, dtype=torch.float32, device=dl.device)
+    _call("ccd_seg_cls_wgrad", _p(u2), _p(_chk(dl, torch.float32)), _p(buf), _p(buf[2304:]), n_img, _s())
+    return buf[:2304].view(2, 128, 3, 3), buf[2304:]

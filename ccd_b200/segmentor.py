@@ -187,15 +187,8 @@ class SegHeadFn(torch.autograd.Function):
                               16, 64, 128, 1, n, taps, 128, rowmap=1, py=py, px=px)
         u2 = torch.empty(M2, 128, **b16)
         st_u2 = _bn_forward(mod.unpool2[1], zu2, 128, M2, 128, u2, 128, training)
-        # cls: conv3x3 128 -> 2 (outputs padded to 8 columns)
-        wc, bc = params[26].detach(), params[27].detach()
-        wcf = torch.zeros(8, 9 * 128, **b16)
-        wcf[:2] = wc.permute(0, 2, 3, 1).reshape(2, 9 * 128)
-        bc8 = torch.zeros(8, dtype=torch.float32, device=dev)
-        bc8[:2] = bc
-        out8 = torch.empty(M2, 8, dtype=torch.float32, device=dev)
-        ops.conv_gemm(u2, wcf, M2, 8, 9 * 128, ops.EPI_F32, bc8, out8, 8, 1, 1, 32, 128, 128, 1, n, CONV3_FWD_TAPS, 128)
-        logits = out8[:, :2].reshape(n, 32, 128, 2).permute(0, 3, 1, 2).contiguous()
+        # cls: conv3x3 128 -> 2, CUDA-core kernel (fp32 weights, NCHW fp32 logits)
+        logits = ops.seg_cls_fwd(u2, params[26].detach().float().contiguous(), params[27].detach().float().contiguous(), n)
         if any(ctx.needs_input_grad):
             saved["bn"] += [st_u1, st_u2]
             ctx.mod, ctx.E, ctx.params = mod, E, params
@@ -216,21 +209,10 @@ class SegHeadFn(torch.autograd.Function):
         grads = [None] * len(params)
         st = saved["bn"]
         # ---- cls ----
-        d8 = torch.zeros(M2, 8, **b16)
-        d8[:, :2] = d_logits.permute(0, 2, 3, 1).reshape(M2, 2)
-        wc = params[26].detach()
-        gb = torch.zeros(8, **f32)
-        ops.colsum_bf16(d8, gb)
-        grads[27] = gb[:2].clone()
-        gw = torch.zeros(8, 9 * 128, **f32)
-        ops.conv_gemm(u2, d8, 8, 9 * 128, M2, ops.EPI_F32, None, gw, 9 * 128, ops.wgrad_splits(128, 9 * 128, M2), 2, 32, 128, 128, 1, n,
-                      CONV3_FWD_TAPS, 128)
-        grads[26] = gw[:2].reshape(2, 3, 3, 128).permute(0, 3, 1, 2).contiguous()
-        wd = torch.zeros(128, 9, 64, **b16)                                     # [c][tap][o padded to 64]
-        wd[:, :, :2] = wc.permute(1, 2, 3, 0).reshape(128, 9, 2)
-        du2 = torch.empty(M2, 128, **b16)
-        ops.conv_gemm(d8, wd.reshape(128, 9 * 64), M2, 128, 9 * 64, ops.EPI_BF16, None, du2, 128, 1, 1, 32, 128, 8, 1, n,
-                      CONV3_DGRAD_TAPS, 64)
+        wc = params[26].detach().float().contiguous()
+        dl = d_logits.float().contiguous()
+        grads[26], grads[27] = ops.seg_cls_wgrad(u2, dl, n)
+        du2 = ops.seg_cls_dgrad(dl, wc, n)
         # ---- unpool2 ----
         dz2, grads[24], grads[25] = _bn_backward(mod.unpool2[1], du2, 128, zu2, 128, *st[7], M2, 128)
         grads[23] = ops.colsum_bf16(dz2, torch.zeros(128, **f32))

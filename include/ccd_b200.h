@@ -133,6 +133,12 @@ int ccd_bn_bwd_apply(const void* dy, int dy_is_f32, int lddy, const void* x, int
                      const float* gamma, const float* beta, const float* sums, float inv_m, void* dx, int lddx, int M, int C,
                      void* stream);
 
+/* cls = Conv2d(128 -> 2, 3x3, pad 1) of the SegHead (segmentor.py:88,94) on the [n,32,128,128] bf16 NHWC map: CUDA-core kernels
+ * (two output channels cannot fill a tensor-core tile).  w = fp32 [2,128,3,3] (torch layout), logits / dl = fp32 NCHW [n,2,32,128]. */
+int ccd_seg_cls_fwd(const void* u2, const float* w, const float* bias, float* logits, int n_img, void* stream);
+int ccd_seg_cls_dgrad(const float* dl, const float* w, void* du2_bf16, int n_img, void* stream);
+int ccd_seg_cls_wgrad(const void* u2, const float* dl, float* dw_zeroed, float* dbias_zeroed, int n_img, void* stream);
+
 /* debug / A-B switches (process-global): key 0 = GEMM variant (1 = persistent [default], 0 = one tile per CTA) */
 int ccd_set_option(int key, int value);
 

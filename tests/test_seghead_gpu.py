@@ -107,6 +107,26 @@ def test_batchnorm_relu_fwd_bwd(ops):
     assert _rel(dz.float(), zr.grad) < 1e-2
 
 
+@pytest.mark.parametrize("n", [1, 3])
+def test_cls_conv_cuda_core_kernels(ops, n):
+    """cls = Conv2d(128 -> 2, 3x3, pad 1) (segmentor.py:88,94): forward, data and weight/bias gradients against F.conv2d."""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(n, 128, 32, 128, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(2, 128, 3, 3, device="cuda", generator=g) * 0.05
+    b = torch.randn(2, device="cuda", generator=g)
+    xm = _nhwc(x)
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=1)
+    out = ops.seg_cls_fwd(xm, w, b, n)
+    assert out.shape == ref.shape and _rel(out, ref) < 1e-5
+    dl = torch.randn(n, 2, 32, 128, device="cuda", generator=g)
+    (ref * dl).sum().backward()
+    dx = ops.seg_cls_dgrad(dl, w, n)
+    assert _rel(dx.float(), _nhwc(xr.grad)) < 4e-3          # bf16 output rounding
+    dw, db = ops.seg_cls_wgrad(xm, dl, n)
+    assert _rel(dw, wr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+
+
 @pytest.mark.parametrize("E", [192, 384])
 def test_seghead_against_oracle(E):
     """Whole SegHead forward + backward (training-mode BN) against the oracle restatement in fp32 on the same weights."""
