@@ -21,7 +21,7 @@ namespace ccd {
 
 enum GemmEpi {
   EPI_BF16 = 0,    // out0 bf16 = acc + bias
-  EPI_GELU = 1,    // out0 bf16 = acc + bias (pre-activation), out1 bf16 = gelu(out0)
+  EPI_GELU = 1,    // out0 bf16 = acc + bias (pre-activation; optional, NULL when no backward follows), out1 bf16 = gelu(out0)
   EPI_RESID = 2,   // out0 f32  = aux_f32[m,n] + acc + bias            (residual stream)
   EPI_F32 = 3,     // out0 f32  = acc + bias   (atomicAdd when split-K)
   EPI_DGELU = 4,   // out0 bf16 = acc * gelu'(aux_bf16[m,n])           (backward through GELU)
@@ -109,8 +109,8 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int row, int c
   if constexpr (EPI == EPI_BF16) {
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   } else if constexpr (EPI == EPI_GELU) {
-    const uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = o;
+    if (p.out0 != nullptr)       // inference (teacher): only the activation is needed
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out1) + off) =
         make_uint2(pack_bf16x2(gelu_fast(v.x), gelu_fast(v.y)), pack_bf16x2(gelu_fast(v.z), gelu_fast(v.w)));
   } else if constexpr (EPI == EPI_RESID) {
@@ -617,7 +617,7 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
                              const float* bias, void* out0, void* out1, const void* aux, const float* seq_scale,
                              int ldc, int splits, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || epi < 0 || epi >= EPI_COUNT || !A || !B || !out0) return CCD_ERR_ARG;
+  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || epi < 0 || epi >= EPI_COUNT || !A || !B || (!out0 && epi != EPI_GELU)) return CCD_ERR_ARG;
   if (ldc <= 0) ldc = N;
   if ((epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_POS) && !aux) return CCD_ERR_ARG;
   if (epi == EPI_GELU && !out1) return CCD_ERR_ARG;

@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------------------
 // out[c] += sum_r x[r,c]   (bias gradients), x bf16 [rows, cols], cols % 8 == 0, out pre-zeroed
 // ---------------------------------------------------------------------------------------------------------
-constexpr int CS_ROWS_PER_BLOCK = 256;
+constexpr int CS_ROWS_PER_BLOCK = 512;
+constexpr int CS_BATCH = 8;           // independent 16 B loads in flight per thread
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows,
                                                           int cols) {
   __shared__ float red[8][32][8];
@@ -210,23 +211,32 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
   const int r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cg * 8 < cols) {
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(x + (size_t)r * cols + cg * 8);
-      a[0] += bf16lo(v.x); a[1] += bf16hi(v.x); a[2] += bf16lo(v.y); a[3] += bf16hi(v.y);
-      a[4] += bf16lo(v.z); a[5] += bf16hi(v.z); a[6] += bf16lo(v.w); a[7] += bf16hi(v.w);
+    const bf16* base = x + (size_t)cg * 8;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8 * CS_BATCH) {
+      uint4 v[CS_BATCH];
+#pragma unroll
+      for (int j = 0; j < CS_BATCH; ++j) {
+        const int rr = r + 8 * j;
+        v[j] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)rr * cols)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < CS_BATCH; ++j) {
+        a[0] += bf16lo(v[j].x); a[1] += bf16hi(v[j].x); a[2] += bf16lo(v[j].y); a[3] += bf16hi(v[j].y);
+        a[4] += bf16lo(v[j].z); a[5] += bf16hi(v[j].z); a[6] += bf16lo(v[j].w); a[7] += bf16hi(v[j].w);
+      }
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = a[j];
   __syncthreads();
-  if (threadIdx.y == 0 && cg * 8 < cols) {
+  // 256 threads reduce the 8 row-lanes of the 256 columns of this block: one atomic per column per block
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int col = blockIdx.x * 256 + t;
+  if (col < cols) {
+    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = 0.f;
-#pragma unroll
-      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][j];
-      atomicAdd(out + cg * 8 + j, t);
-    }
+    for (int y = 0; y < 8; ++y) sum += red[y][t >> 3][t & 7];
+    atomicAdd(out + col, sum);
   }
 }
 

@@ -190,7 +190,7 @@ class VitFn(torch.autograd.Function):
             x2 = torch.empty(T, E, **f32)
             ops.linear_fwd(o, wproj, bproj, ops.EPI_RESID, x2, None, x, seq_scale=ds_attn)
             xn2, _ = ops.layernorm_fwd(x2, g2, b2)
-            hpre = torch.empty(T, 4 * E, **b16)
+            hpre = torch.empty(T, 4 * E, **b16) if save else None      # pre-activation only feeds the backward
             hact = torch.empty(T, 4 * E, **b16)
             ops.linear_fwd(xn2, wfc1, bfc1, ops.EPI_GELU, hpre, hact)
             x3 = torch.empty(T, E, **f32)

@@ -25,7 +25,7 @@ extern "C" {
 
 /* ---- GEMM epilogues (ccd_gemm_bf16 `epi`) ---- */
 #define CCD_EPI_BF16 0  /* out0 bf16 = acc + bias                                                   */
-#define CCD_EPI_GELU 1  /* out0 bf16 = acc + bias ; out1 bf16 = gelu_erf(out0)     (Mlp.fc1+act, vision_transformer.py:59-61) */
+#define CCD_EPI_GELU 1  /* out0 bf16 = acc + bias (may be NULL: inference) ; out1 bf16 = gelu_erf(acc + bias)  (Mlp.fc1+act, vision_transformer.py:59-61) */
 #define CCD_EPI_RESID 2 /* out0 f32 = aux_f32 + s[m/256]*(acc + bias); s = DropPath keep-scale (vision_transformer.py:27-36) or NULL;                         (x = x + f(x), vision_transformer.py:109-110) */
 #define CCD_EPI_F32 3   /* out0 f32 = acc + bias ; split-K slices accumulate atomically (caller zero-fills)  */
 #define CCD_EPI_DGELU 4 /* out0 bf16 = acc * gelu'(aux_bf16)                        (autograd of nn.GELU)   */

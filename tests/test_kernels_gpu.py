@@ -86,6 +86,9 @@ def test_gemm_epilogues(ops, N):
     assert _rel(pre.float(), acc) < 4e-3
     assert (act.float() - O.gelu(pre.float())).abs().max() < 2e-2
     assert _rel(act.float(), O.gelu(pre.float())) < 4e-3
+    act2 = torch.empty_like(pre)                      # inference form: no pre-activation output
+    ops.gemm(A, B, M, N, K, 0, 0, ops.EPI_GELU, bias, None, act2)
+    assert torch.equal(act2, act)
     # residual
     res = torch.randn(M, N, device="cuda", generator=g)
     out = torch.empty(M, N, device="cuda")

@@ -115,12 +115,12 @@ def test_cls_conv_cuda_core_kernels(ops, n):
     w = torch.randn(2, 128, 3, 3, device="cuda", generator=g) * 0.05
     b = torch.randn(2, device="cuda", generator=g)
     xm = _nhwc(x)
-    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    ref = F.conv2d(xr, wr, br, padding=1)
+    xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=1)          # fp64: cuDNN's fp32 convolution may run in TF32
     out = ops.seg_cls_fwd(xm, w, b, n)
     assert out.shape == ref.shape and _rel(out, ref) < 1e-5
     dl = torch.randn(n, 2, 32, 128, device="cuda", generator=g)
-    (ref * dl).sum().backward()
+    (ref * dl.double()).sum().backward()
     dx = ops.seg_cls_dgrad(dl, w, n)
     assert _rel(dx.float(), _nhwc(xr.grad)) < 4e-3          # bf16 output rounding
     dw, db = ops.seg_cls_wgrad(xm, dl, n)
