@@ -106,35 +106,68 @@ class SegHead(nn.Module):           # segmentor.py:73-95
         return SegHeadFn.apply(self, *taps, *params)
 
 
-def _bn_forward(bn, z, ldz, M, C, y, ldy, training):
-    """BatchNorm2d / SyncBatchNorm (training: batch statistics, running-stat update) + ReLU.  Returns (mean, rstd, count)."""
+def _sync(bn):
+    return isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _bn_forward_group(items, training):
+    """BatchNorm2d / SyncBatchNorm (training: batch statistics, running-stat update) + ReLU for several INDEPENDENT layers
+    items = [(bn, z, ldz, M, C, y, ldy)]; under SyncBatchNorm their statistics travel in ONE all-reduce.
+    Returns [(mean, rstd, count)]."""
+    out = []
     if training:
-        sums = ops.bn_stats(z, ldz, M, C)
-        count = float(M)
-        if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(sums)
-            count *= dist.get_world_size()
-        mom = 0.1 if bn.momentum is None else bn.momentum
-        mean, rstd = ops.bn_finalize(sums, count, bn.eps, mom, bn.running_mean if bn.track_running_stats else None,
-                                     bn.running_var if bn.track_running_stats else None, C)
-        if bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        sums = [ops.bn_stats(z, ldz, M, C) for (_, z, ldz, M, C, _, _) in items]
+        world = 1
+        if _sync(items[0][0]):
+            world = dist.get_world_size()
+            if len(sums) > 1:
+                flat = torch.cat(sums)
+                dist.all_reduce(flat)
+                sums = list(flat.split([t.numel() for t in sums]))
+            else:
+                dist.all_reduce(sums[0])
+        for (bn, z, ldz, M, C, y, ldy), sm in zip(items, sums):
+            count = float(M) * world
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            mean, rstd = ops.bn_finalize(sm, count, bn.eps, mom, bn.running_mean if bn.track_running_stats else None,
+                                         bn.running_var if bn.track_running_stats else None, C)
+            if bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            out.append((mean, rstd, count))
     else:
-        mean = bn.running_mean.float()
-        rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
-        count = float(M)
-    ops.bn_apply_relu(z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), y, ldy, M, C)
-    return mean, rstd, count
+        for (bn, z, ldz, M, C, y, ldy) in items:
+            out.append((bn.running_mean.float(), torch.rsqrt(bn.running_var.float() + bn.eps), float(M)))
+    for (bn, z, ldz, M, C, y, ldy), (mean, rstd, _) in zip(items, out):
+        ops.bn_apply_relu(z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), y, ldy, M, C)
+    return out
+
+
+def _bn_forward(bn, z, ldz, M, C, y, ldy, training):
+    return _bn_forward_group([(bn, z, ldz, M, C, y, ldy)], training)[0]
+
+
+def _bn_backward_group(items):
+    """items = [(bn, dy, lddy, z, ldz, mean, rstd, count, M, C)] of independent layers -> [(dz bf16 [M,C], dgamma, dbeta)]."""
+    sums = [ops.bn_bwd_reduce(dy, lddy, z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), M, C)
+            for (bn, dy, lddy, z, ldz, mean, rstd, count, M, C) in items]
+    # local sums = parameter gradients (dgamma, dbeta); DDP averages them across ranks
+    pgrads = [(sm[it[9]:].clone(), sm[:it[9]].clone()) for sm, it in zip(sums, items)]
+    if _sync(items[0][0]):
+        if len(sums) > 1:
+            flat = torch.cat(sums)
+            dist.all_reduce(flat)
+            sums = list(flat.split([t.numel() for t in sums]))
+        else:
+            dist.all_reduce(sums[0])
+    out = []
+    for (bn, dy, lddy, z, ldz, mean, rstd, count, M, C), sm, (dgamma, dbeta) in zip(items, sums, pgrads):
+        dz = ops.bn_bwd_apply(dy, lddy, z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), sm, 1.0 / count, M, C)
+        out.append((dz, dgamma, dbeta))
+    return out
 
 
 def _bn_backward(bn, dy, lddy, z, ldz, mean, rstd, count, M, C):
-    """-> (dz bf16 [M,C], dgamma, dbeta)."""
-    sums = ops.bn_bwd_reduce(dy, lddy, z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), M, C)
-    dbeta, dgamma = sums[:C].clone(), sums[C:].clone()          # local sums = parameter gradients (DDP averages them)
-    if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(sums)
-    dz = ops.bn_bwd_apply(dy, lddy, z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), sums, 1.0 / count, M, C)
-    return dz, dgamma, dbeta
+    return _bn_backward_group([(bn, dy, lddy, z, ldz, mean, rstd, count, M, C)])[0]
 
 
 class SegHeadFn(torch.autograd.Function):
@@ -153,18 +186,22 @@ class SegHeadFn(torch.autograd.Function):
         cat = torch.empty(T, 192, **b16)
         xs, zas, acts, zbs = [], [], [], []
         for i, (br, tap) in enumerate(zip(branches, (t0, t1, t2))):
-            w0, w3 = params[6 * i].detach(), params[6 * i + 3].detach()
+            w0 = params[6 * i].detach()
             x = ops.cast_bf16(tap.contiguous().float()) if tap.dtype != torch.bfloat16 else tap.contiguous()
             wf = w0.permute(0, 2, 3, 1).reshape(128, 9 * E).to(torch.bfloat16).contiguous()         # [o][tap][c]
             za = torch.empty(T, 128, **b16)
             ops.conv_gemm(x, wf, T, 128, 9 * E, ops.EPI_BF16, None, za, 128, 1, 1, 8, 32, E, 1, n, CONV3_FWD_TAPS, E)
-            a = torch.empty(T, 128, **b16)
-            st_a = _bn_forward(br[1], za, 128, T, 128, a, 128, training)
+            xs.append(x); zas.append(za); acts.append(torch.empty(T, 128, **b16))
+        # the three branches are independent: their BatchNorm statistics share one (Sync)BN exchange per level
+        st_as = _bn_forward_group([(br[1], zas[i], 128, T, 128, acts[i], 128) for i, br in enumerate(branches)], training)
+        for i, br in enumerate(branches):
+            w3 = params[6 * i + 3].detach()
             zb = torch.empty(T, 64, **b16)
-            ops.linear_fwd(a, w3.reshape(64, 128).to(torch.bfloat16).contiguous(), None, ops.EPI_BF16, zb)
-            st_b = _bn_forward(br[4], zb, 64, T, 64, cat[:, 64 * i:], 192, training)
-            xs.append(x); zas.append(za); acts.append(a); zbs.append(zb)
-            saved["bn"] += [st_a, st_b]
+            ops.linear_fwd(acts[i], w3.reshape(64, 128).to(torch.bfloat16).contiguous(), None, ops.EPI_BF16, zb)
+            zbs.append(zb)
+        st_bs = _bn_forward_group([(br[4], zbs[i], 64, T, 64, cat[:, 64 * i:], 192) for i, br in enumerate(branches)], training)
+        for i in range(3):
+            saved["bn"] += [st_as[i], st_bs[i]]
         # unpool1: ConvTranspose2d(192 -> 128) 8x32 -> 16x64, four parity GEMMs
         wu1, bu1 = params[18].detach(), params[19].detach()
         zu1 = torch.empty(M1, 128, **b16)
@@ -238,15 +275,21 @@ class SegHeadFn(torch.autograd.Function):
         ops.conv_gemm(dz1, wd1, T, 192, 16 * 128, ops.EPI_BF16, None, dcat, 192, 1, 1, 8, 32, 256, 2, n, tb, 128)
         # ---- the three branches ----
         d_taps = []
+        rb = _bn_backward_group([(br[4], dcat[:, 64 * i:], 192, zbs[i], 64, *st[2 * i + 1], T, 64) for i, br in enumerate(branches)])
+        das = []
         for i, br in enumerate(branches):
-            w0, w3 = params[6 * i].detach(), params[6 * i + 3].detach()
-            dzb, grads[6 * i + 4], grads[6 * i + 5] = _bn_backward(br[4], dcat[:, 64 * i:], 192, zbs[i], 64, *st[2 * i + 1], T, 64)
+            w3 = params[6 * i + 3].detach()
+            dzb, grads[6 * i + 4], grads[6 * i + 5] = rb[i]
             gw3 = torch.zeros(64, 128, **f32)
             ops.linear_wgrad(dzb, acts[i], gw3)
             grads[6 * i + 3] = gw3.reshape(64, 128, 1, 1)
             da = torch.empty(T, 128, **b16)
             ops.linear_dgrad(dzb, w3.reshape(64, 128).to(torch.bfloat16).contiguous(), ops.EPI_BF16, da)
-            dza, grads[6 * i + 1], grads[6 * i + 2] = _bn_backward(br[1], da, 128, zas[i], 128, *st[2 * i], T, 128)
+            das.append(da)
+        ra = _bn_backward_group([(br[1], das[i], 128, zas[i], 128, *st[2 * i], T, 128) for i, br in enumerate(branches)])
+        for i, br in enumerate(branches):
+            w0 = params[6 * i].detach()
+            dza, grads[6 * i + 1], grads[6 * i + 2] = ra[i]
             gw0 = torch.zeros(128, 9 * E, **f32)
             ops.conv_gemm(xs[i], dza, 128, 9 * E, T, ops.EPI_F32, None, gw0, 9 * E, ops.wgrad_splits(128, 9 * E, T), 2, 8, 32, E, 1, n,
                           CONV3_FWD_TAPS, E)

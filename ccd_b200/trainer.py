@@ -44,8 +44,11 @@ class PretrainStep:
             # static_graph=True gives the same semantics without re-walking the autograd graph every iteration
             student = nn.parallel.DistributedDataParallel(student, device_ids=[self.device.index],
                                                           find_unused_parameters=True,
+                                                          gradient_as_bucket_view=os.environ.get("CCD_DDP_BUCKET_VIEW", "1") == "1",
                                                           static_graph=os.environ.get("CCD_DDP_STATIC", "1") == "1")
         self.student, self.teacher = student, teacher
+        self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        self._loss_event = torch.cuda.Event()
         teacher.backbone.load_state_dict(self.student_module.backbone.state_dict())                           # :109-110
         teacher.head.load_state_dict(self.student_module.head.state_dict())
         for p in teacher.parameters():
@@ -76,8 +79,12 @@ class PretrainStep:
         masks_image = ops.warp_mask(masks.contiguous().float(), metrics.contiguous())                         # :234-236
         so["gt"] = [masks, masks_image]
         loss = self.loss(so, to, epoch)                                                                       # :238
-        if sync_loss and not math.isfinite(loss.item()):                                                      # :239-241
-            raise FloatingPointError(f"Loss is {loss.item()}, stopping training")
+        if sync_loss:
+            # train.py:239-241 reads loss.item() here and exits on a non-finite value.  The read is issued here but
+            # awaited only after the rest of the step has been queued, so the GPU never idles on the host round trip;
+            # the process stops on the same iteration either way.
+            self._loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            self._loss_event.record()
         self.opt.zero_grad(set_to_none=True)                                                                  # :244
         loss.backward()                                                                                       # :247
         if self.clip_grad:
@@ -86,4 +93,8 @@ class PretrainStep:
         self.opt.step()                                                                                       # :252
         self.ema.step(float(self.mom_sched[it]))                                                              # :264-272
         self.iteration += 1
+        if sync_loss:
+            self._loss_event.synchronize()
+            if not math.isfinite(float(self._loss_host[0])):
+                raise FloatingPointError(f"Loss is {float(self._loss_host[0])}, stopping training")
         return loss
