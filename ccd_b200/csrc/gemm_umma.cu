@@ -17,6 +17,12 @@
 #include "ccd_common.cuh"
 #include "tmap.cuh"
 
+// Experiment switches (tools/build_variants.py builds extra libraries with -DCCD_DBG_EPI=n; never set in the product build):
+//   1 = epilogue computes but never stores, 2 = GELU / GELU' replaced by the identity, 3 = epilogue only drains TMEM
+#ifndef CCD_DBG_EPI
+#define CCD_DBG_EPI 0
+#endif
+
 namespace ccd {
 
 enum GemmEpi {
@@ -90,15 +96,74 @@ __device__ __forceinline__ float gelu_sigmoid(float x, float& xc_out, float& x2_
   return __fdividef(1.0f, 1.0f + e);
 }
 __device__ __forceinline__ float gelu_fast(float x) {
+#if CCD_DBG_EPI == 2
+  return x;
+#endif
   float xc, x2;
   return x * gelu_sigmoid(x, xc, x2);
 }
 __device__ __forceinline__ float dgelu_fast(float x) {      // d/dx [x sigma(v)] = sigma + x sigma (1 - sigma) v'(x)
+#if CCD_DBG_EPI == 2
+  return x;
+#endif
   float xc, x2;
   const float sg = gelu_sigmoid(x, xc, x2);
   float vp = fmaf(x2, -3.5151679e-3f, 0.22203388f);       // 5c , 3b
   vp = fmaf(x2, vp, 1.5950158f);                           // a
   return fmaf(xc * sg * (1.0f - sg), vp, sg);
+}
+
+// Packed (fp32x2) forms used by the persistent kernel's epilogues: the same polynomial, evaluated two elements per
+// instruction (FMUL2 / FFMA2) with sigma(v) = 1/2 + 1/2 tanh(v/2) on ONE MUFU.TANH instead of MUFU.EX2 + MUFU.RCP, and the
+// argument clamp moved onto x^2 (one FMNMX): for |x| > 8 the polynomial is frozen at its value at 8, where sigma has
+// long saturated.  7-8.5 issue slots per element instead of 15-16 (the GELU epilogues are instruction-issue / latency
+// bound: profiles/).   CCD_GELU_TANH=0 keeps the scalar ex2/rcp form.
+#ifndef CCD_GELU_TANH
+#define CCD_GELU_TANH 1
+#endif
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+#if CCD_DBG_EPI == 2
+  return x;
+#elif CCD_GELU_TANH
+  float2 x2 = __fmul2_rn(x, x);
+  x2.x = fminf(x2.x, 64.0f);
+  x2.y = fminf(x2.y, 64.0f);
+  float2 pl = __ffma2_rn(x2, f2(-3.5151679e-4f), f2(0.037005647f));     // c/2 , b/2
+  pl = __ffma2_rn(x2, pl, f2(0.7975079f));                                // a/2
+  const float2 w = __fmul2_rn(x, pl);                                     // v(x) / 2
+  const float2 h = __fmul2_rn(x, f2(0.5f));
+  const float2 t = make_float2(tanh_approx(w.x), tanh_approx(w.y));
+  return __ffma2_rn(h, t, h);                                             // x (1/2 + 1/2 tanh(v/2))
+#else
+  return make_float2(gelu_fast(x.x), gelu_fast(x.y));
+#endif
+}
+__device__ __forceinline__ float2 dgelu_fast2(float2 x) {   // sigma + x sigma (1 - sigma) v'(x), sigma (1 - sigma) = (1 - t^2) / 4
+#if CCD_DBG_EPI == 2
+  return x;
+#elif CCD_GELU_TANH
+  float2 x2 = __fmul2_rn(x, x);
+  x2.x = fminf(x2.x, 64.0f);
+  x2.y = fminf(x2.y, 64.0f);
+  float2 pl = __ffma2_rn(x2, f2(-3.5151679e-4f), f2(0.037005647f));
+  pl = __ffma2_rn(x2, pl, f2(0.7975079f));
+  float2 vq = __ffma2_rn(x2, f2(-8.7879198e-4f), f2(0.05550847f));       // v'(x) / 4 :  5c/4 , 3b/4
+  vq = __ffma2_rn(x2, vq, f2(0.39875395f));                               // a/4
+  const float2 w = __fmul2_rn(x, pl);
+  const float2 u = __fmul2_rn(x, vq);
+  const float2 t = make_float2(tanh_approx(w.x), tanh_approx(w.y));
+  const float2 omt2 = __ffma2_rn(make_float2(-t.x, -t.y), t, f2(1.0f));
+  const float2 sg = __ffma2_rn(t, f2(0.5f), f2(0.5f));
+  return __ffma2_rn(u, omt2, sg);
+#else
+  return make_float2(dgelu_fast(x.x), dgelu_fast(x.y));
+#endif
 }
 
 // Phase 2 of the epilogue: one output row per iteration, lane l owns columns [4l, 4l+4) -> every global access of the
@@ -111,8 +176,8 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, int row, int c
   } else if constexpr (EPI == EPI_GELU) {
     if (p.out0 != nullptr)       // inference (teacher): only the activation is needed
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out1) + off) =
-        make_uint2(pack_bf16x2(gelu_fast(v.x), gelu_fast(v.y)), pack_bf16x2(gelu_fast(v.z), gelu_fast(v.w)));
+    const float2 g0 = gelu_fast2(make_float2(v.x, v.y)), g1 = gelu_fast2(make_float2(v.z, v.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out1) + off) = make_uint2(pack_bf16x2(g0.x, g0.y), pack_bf16x2(g1.x, g1.y));
   } else if constexpr (EPI == EPI_RESID) {
     const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + off);
     if (p.seq_scale != nullptr) {
@@ -303,6 +368,17 @@ struct PgWork {
 
 template <int EPI> struct AuxPack { uint32_t a, b, c, d; };
 
+// explicit shared-space accesses for the epilogue transpose (the generic-pointer form compiles to LD.E / ST.E, which are
+// tracked on the long scoreboard like global loads)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
 template <int EPI>
 __device__ __forceinline__ AuxPack<EPI> aux_load(const GemmParams& p, int row, int col) {
   AuxPack<EPI> r{0u, 0u, 0u, 0u};
@@ -321,6 +397,12 @@ __device__ __forceinline__ AuxPack<EPI> aux_load(const GemmParams& p, int row, i
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, int col, float4 v, const AuxPack<EPI>& x) {
+#if CCD_DBG_EPI == 1
+  if (__float_as_uint(v.x) != 0x7fc12345u) {       // never true for real data: keeps the math, drops the stores
+    v.x = v.y + v.z;
+    if (__float_as_uint(v.x) != 0x7fc12346u) return;
+  }
+#endif
   const size_t off = (size_t)row * p.ldc + col;
   if constexpr (EPI == EPI_RESID) {
     if (p.seq_scale != nullptr) {
@@ -330,9 +412,9 @@ __device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, i
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + off) =
         make_float4(v.x + __uint_as_float(x.a), v.y + __uint_as_float(x.b), v.z + __uint_as_float(x.c), v.w + __uint_as_float(x.d));
   } else if constexpr (EPI == EPI_DGELU) {
-    v.x *= dgelu_fast(bf16lo(x.a)); v.y *= dgelu_fast(bf16hi(x.a));
-    v.z *= dgelu_fast(bf16lo(x.b)); v.w *= dgelu_fast(bf16hi(x.b));
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const float2 d0 = __fmul2_rn(make_float2(v.x, v.y), dgelu_fast2(make_float2(bf16lo(x.a), bf16hi(x.a))));
+    const float2 d1 = __fmul2_rn(make_float2(v.z, v.w), dgelu_fast2(make_float2(bf16lo(x.b), bf16hi(x.b))));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(d0.x, d0.y), pack_bf16x2(d1.x, d1.y));
   } else if constexpr (EPI == EPI_POS) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + off) =
         make_float4(v.x + __uint_as_float(x.a), v.y + __uint_as_float(x.b), v.z + __uint_as_float(x.c), v.w + __uint_as_float(x.d));
@@ -342,7 +424,7 @@ __device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, i
 }
 
 template <int EPI, int BN, bool SPATIAL>
-__global__ void __launch_bounds__(PG_THREADS, 1)
+__global__ void __launch_bounds__(PG_THREADS, 1)   // 168 registers: warps are allocated in groups of 4 (12 x 32 x 168 <= 64 K)
 gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const GemmParams p_in, const PgWork wk, const ConvSpec cs) {
   using Cfg = PgCfg<BN>;
@@ -367,7 +449,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 256);              // both epilogue warpgroups read every accumulator
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -473,13 +555,17 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: group g takes items it = g, g+2, ... of this CTA (accumulator it & 1 == g) =====================
+    // ===================== epilogue: BOTH warpgroups work on every tile (group g takes column chunks [g, g+1) * BN/64) =====================
+    // With one warpgroup per tile the accumulator was held for the whole epilogue E of a tile and the tile period was
+    // (M + E) / 2 with E ~ 3 M (ncu: the epilogue warps spent 20 % of their time waiting for the next accumulator while
+    // the MMA issuer waited for them).  Two warps per scheduler on the same tile halve the time an accumulator is held
+    // and double the latency hiding: period = max(M, E / 2).
     const int g = (warp - 3) >> 2;
+    constexpr int CHUNKS_PER_GROUP = BN / 64;
     const int q = warp & 3;                                       // TMEM lane quarter this warp may read
     float* stage = reinterpret_cast<float*>(staging + (warp - 3) * PG_STAGING);
     int it = 0;
     for (int item = blockIdx.x; item < wk.n_items; item += gridDim.x, ++it) {
-      if ((it & 1) != g) continue;
       GemmParams p = p_in;
       const int z = item / wk.n_tiles, tile = item - z * wk.n_tiles;
       if (z != 0) p.bias = nullptr;
@@ -494,16 +580,69 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         constexpr int ES = (EPI == EPI_RESID) ? 4 : 2;
         const int prow = row_base + lane;
         if (prow < p.M) {
-          const char* base = reinterpret_cast<const char*>(p.aux) + ((size_t)prow * p.ldc + n0) * ES;
-          const int bytes = min(BN, p.N - n0) * ES;
+          const int nb = n0 + g * (BN / 2);
+          const char* base = reinterpret_cast<const char*>(p.aux) + ((size_t)prow * p.ldc + nb) * ES;
+          const int bytes = max(0, min(BN / 2, p.N - nb)) * ES;
           for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
         }
       }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
+      // Full tiles (every row and column valid) take a branch-free path: all eight staging loads of a chunk are issued
+      // back to back, then the 32 independent epilogue chains, then the stores.  (The masked path below serialises
+      // load -> math -> store per row group; measured with ncu source counters it made the GELU / GELU' / residual
+      // epilogues latency bound at ~1600 cycles per 32-column chunk, 4x the MMA time of the tile.)
+      const bool full = (row_base + 32 <= p.M) && (n0 + BN <= p.N);
+      const uint32_t stage_s = smem_u32(stage);
+      const uint32_t st_wr = stage_s + (uint32_t)lane * 128u;                      // thread = row `lane` of the chunk
+      const uint32_t st_rd = stage_s + (uint32_t)sub_row * 128u + (uint32_t)((sub_chunk ^ (sub_row & 7)) * 16);
+      const int c_begin = g * CHUNKS_PER_GROUP, c_end = c_begin + CHUNKS_PER_GROUP;
+      // bias of the next chunk is requested one chunk ahead (its global-load latency was exposed in every chunk)
+      float4 b4_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (full && p.bias != nullptr) b4_next = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c_begin * 32 + 4 * sub_chunk));
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         const int col = n0 + c * 32 + 4 * sub_chunk;
+        if (full) {
+          AuxPack<EPI> ax[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ax[i] = aux_load<EPI>(p, row_base + i * 4 + sub_row, col);
+          const float4 b4 = b4_next;
+          if (p.bias != nullptr && c + 1 < c_end) b4_next = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32));
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), raw);
+          tmem_wait_ld();
+          if (c == c_end - 1) {                  // this group's half of the accumulator is read: hand it back to the MMA issuer
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+#if CCD_DBG_EPI == 3
+          if (raw[0] != 0x7fc12345u) continue;
+#endif
+#pragma unroll
+          for (int j = 0; j < 8; ++j)            // 16-byte chunk j of row `lane` lands at j ^ (lane & 7)
+            sts128(st_wr + (uint32_t)((j ^ (lane & 7)) * 16), raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+          __syncwarp();
+          float4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {          // rows r = 4 i + sub_row: (r & 7) = ((4 i) & 7) | sub_row -> chunk index ^ 4 on odd i
+            v[i] = lds128((st_rd + (uint32_t)i * 512u) ^ ((i & 1) ? 64u : 0u));
+            v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
+          }
+          __syncwarp();                          // the 4 KB transpose buffer is rewritten by the next chunk
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int orow = row_base + i * 4 + sub_row;
+            if (SPATIAL && cs.out_rowmap) {      // ConvTranspose2d stride 2: scatter to the (py, px) parity positions
+              const int hw = cs.H * cs.W;
+              const int n_img = orow / hw, rem = orow - n_img * hw;
+              const int a = rem / cs.W, b = rem - a * cs.W;
+              orow = (n_img * 2 * cs.H + 2 * a + cs.py) * (2 * cs.W) + 2 * b + cs.px;
+            }
+            epilogue_row_aux<EPI>(p, orow, col, v[i], ax[i]);
+          }
+          continue;
+        }
         const bool col_ok = col < p.N;
         // auxiliary operands + bias of this chunk are requested first: their latency hides behind the transpose
         AuxPack<EPI> ax[8];
@@ -515,7 +654,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), raw);
         tmem_wait_ld();
-        if (c == BN / 32 - 1) {                  // accumulator fully read: hand it back to the MMA issuer
+        if (c == c_end - 1) {                    // this group's half of the accumulator is read: hand it back to the MMA issuer
           tc_fence_before();
           mbar_arrive(&tmem_empty[acc]);
         }

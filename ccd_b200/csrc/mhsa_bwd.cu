@@ -270,6 +270,272 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined, persistent variant (default).  ncu on the kernel above: 53 % of the warp samples wait for an accumulator
+// (S^T/dP^T ready, previous pair retired) and 13 % at the CTA's exit barrier, tensor pipe 14 % -- the five contractions
+// and the softmax-gradient math of a pair ran strictly one after the other, and every CTA paid its 128 KB load,
+// TMEM allocation and epilogue unoverlapped.  Here:
+//   * one CTA per SM walks (sequence, head) items; the TMA loads of item n+1 are issued as soon as the last MMA of item n
+//     has retired and overlap its dK/dV/dQ epilogue;
+//   * the pair loop runs over 64-query sub-tiles s = 0..7 (key tile j = s / 4, queries [64 (s % 4), +64)):
+//     S^T_s / dP^T_s (64 fp32 columns each) live in TMEM stage s & 1, so the MMAs of sub-tile s+1 run while warpgroup
+//     s & 1 does the softmax-gradient math of sub-tile s (the two warpgroups ping-pong);
+//   * P^T goes back to TMEM as the bf16 A operand of dV (over the S^T columns it came from); only dS^T passes through
+//     shared memory (K-major A of dK, MN-major A of dQ), four 16 KB sub-blocks that are recycled per key tile;
+//   * TMEM: stage 0 [0,128) stage 1 [128,256) | dK [256,320) dV [320,384) dQ_0 [384,448) dQ_1 [448,512).
+// ---------------------------------------------------------------------------------------------------------
+struct MhsaBwd2Smem {
+  static constexpr int TILE = ATB_N * ATB_D * 2;  // 32 KB
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = TILE;
+  static constexpr int OFF_V = 2 * TILE;
+  static constexpr int OFF_DO = 3 * TILE;
+  static constexpr int OFF_DS = 4 * TILE;             // 4 sub-blocks [128 keys x 64 queries] bf16, 16 KB each
+  static constexpr int OFF_LSE = 6 * TILE;            // 2 x 256 f32 (double buffered per item): -lse2
+  static constexpr int OFF_DELTA = OFF_LSE + 2048;    // 2 x 256 f32: delta * scale
+  static constexpr int OFF_BAR = OFF_DELTA + 2048;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
+
+__device__ __forceinline__ void sts128_b(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128_b(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(ATB_THREADS, 1)
+mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                          const MhsaBwdParams p, int n_items) {
+  using L = MhsaBwd2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* bar_qk = bars;           // Q, K of the item landed                       (1 completion / item)
+  uint64_t* bar_vdo = bars + 1;      // V, dO landed
+  uint64_t* bar_done = bars + 2;     // every MMA of the item retired: smem reusable   (1 / item)
+  uint64_t* bar_s = bars + 3;        // [2] S^T_s, dP^T_s ready in TMEM stage          (4 / item each)
+  uint64_t* bar_pd = bars + 5;       // [2] P^T (TMEM) and dS^T (smem) of sub-tile written, 128 arrivals (4 / item each)
+  uint64_t* bar_free = bars + 7;     // [4] dS^T sub-block no longer read by an MMA    (2 / item each)
+  uint64_t* bar_acc = bars + 11;     // dK_j, dV_j (and, for j = 1, dQ) complete       (2 / item)
+  uint64_t* bar_epi = bars + 12;     // dK_j / dV_j (+dQ) read out of TMEM, 256 arrivals (2 / item)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_vdo, 1);
+    mbar_init(bar_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_pd[i], 128);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_free[i], 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_epi, 256);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tDK = tmem_base + 256, tDV = tmem_base + 320, tDQ = tmem_base + 384;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int s = w / p.H, h = w - s * p.H;
+        const int row0 = s * ATB_N;
+        mbar_wait(bar_done, (it & 1) ^ 1);            // previous item's MMAs no longer read Q/K/V/dO (passes for it = 0)
+        mbar_arrive_expect_tx(bar_qk, 2 * L::TILE);
+        for (int b = 0; b < 2; ++b) {
+          tma_load_2d(smem + L::OFF_K + b * 16384, &tmQKV, bar_qk, p.E + h * ATB_D, row0 + b * 128);
+          tma_load_2d(smem + L::OFF_Q + b * 16384, &tmQKV, bar_qk, h * ATB_D, row0 + b * 128);
+        }
+        mbar_arrive_expect_tx(bar_vdo, 2 * L::TILE);
+        for (int b = 0; b < 2; ++b) {
+          tma_load_2d(smem + L::OFF_V + b * 16384, &tmQKV, bar_vdo, 2 * p.E + h * ATB_D, row0 + b * 128);
+          tma_load_2d(smem + L::OFF_DO + b * 16384, &tmDO, bar_vdo, h * ATB_D, row0 + b * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t aQ = smem_u32(smem + L::OFF_Q), aK = smem_u32(smem + L::OFF_K), aV = smem_u32(smem + L::OFF_V),
+                     aDO = smem_u32(smem + L::OFF_DO), aDS = smem_u32(smem + L::OFF_DS);
+      const uint32_t id_s = umma_idesc_bf16(128, 64, 0, 0);    // S^T / dP^T sub-tile: K-major x K-major, N = 64 queries
+      const uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dV / dK: A K-major (TMEM or smem), B MN-major
+      const uint32_t id_nn = umma_idesc_bf16(128, 64, 1, 1);   // dQ: A MN-major, B MN-major
+      // sub-tile s: key tile j = s >> 2, queries [64 qs, 64 qs + 64) with qs = s & 3 (row offset qs * 8192 B in Q / dO)
+      auto issue_s = [&](int s) {
+        const int j = s >> 2, qs = s & 3;
+        const uint32_t tS = tmem_base + (s & 1) * 128;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tS, umma_smem_desc_sw128(aK + j * 16384 + ks * 32, 16, 1024),
+                  umma_smem_desc_sw128(aQ + qs * 8192 + ks * 32, 16, 1024), id_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tS + 64, umma_smem_desc_sw128(aV + j * 16384 + ks * 32, 16, 1024),
+                  umma_smem_desc_sw128(aDO + qs * 8192 + ks * 32, 16, 1024), id_s, ks > 0 ? 1u : 0u);
+        umma_commit(&bar_s[s & 1]);
+      };
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        mbar_wait(bar_qk, it & 1);
+        mbar_wait(bar_vdo, it & 1);
+        tc_fence_after();
+        issue_s(0);
+        issue_s(1);
+#pragma unroll 1
+        for (int s = 0; s < 8; ++s) {
+          const int g = s & 1, j = s >> 2, qs = s & 3;
+          mbar_wait(&bar_pd[g], (s >> 1) & 1);
+          if (qs == 0) mbar_wait(bar_epi, j ^ 1);     // dK / dV (dQ) accumulators of the previous key tile / item read out
+          tc_fence_after();
+          const uint32_t tP = tmem_base + g * 128;    // bf16 P^T over the first 32 columns of the stage
+          const uint32_t aDSq = aDS + qs * 16384;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {            // contraction over the 64 queries of the sub-tile
+            // dV_j += P^T dO_s        (dO sub-tile read MN-major: 16 query rows = 2048 B)
+            umma_ts(tDV, tP + ks * 8, umma_smem_desc_sw128(aDO + qs * 8192 + ks * 2048, 8192, 1024), id_kn,
+                    (qs > 0 || ks > 0) ? 1u : 0u);
+            // dK_j += dS^T Q_s
+            umma_ss(tDK, umma_smem_desc_sw128(aDSq + ks * 32, 16, 1024),
+                    umma_smem_desc_sw128(aQ + qs * 8192 + ks * 2048, 8192, 1024), id_kn, (qs > 0 || ks > 0) ? 1u : 0u);
+          }
+          if (qs & 1) {
+            // dQ_I += dS_I K_j over the 128 keys, I = qs >> 1: A = sub-blocks (qs-1, qs) read MN-major (64-query chunks
+            // 16 KB apart, 16 key rows = 2048 B)
+            const int I = qs >> 1;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_ss(tDQ + I * 64, umma_smem_desc_sw128(aDS + I * 32768 + ks * 2048, 16384, 1024),
+                      umma_smem_desc_sw128(aK + j * 16384 + ks * 2048, 8192, 1024), id_nn, (j > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&bar_free[qs - 1]);
+            umma_commit(&bar_free[qs]);
+          }
+          if (qs == 3) umma_commit(bar_acc);
+          if (s == 7) umma_commit(bar_done);
+          if (s + 2 < 8) issue_s(s + 2);              // overwrites stage g: after the dV MMAs above (in-order) and after
+        }                                             // warpgroup g finished reading it (bar_pd)
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax-gradient warpgroups: thread = key row of tile j (TMEM lane) =====================
+    const int g = (warp - 2) >> 2;
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const int tid = g * 128 + r;                      // 0..255 <-> query row for the lse / delta staging
+    const uint32_t sLse = smem_u32(smem + L::OFF_LSE), sDel = smem_u32(smem + L::OFF_DELTA);
+    const uint32_t sDS = smem_u32(smem + L::OFF_DS);
+    const float2 c2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int s_idx = w / p.H, h = w - s_idx * p.H;
+      const int row0 = s_idx * ATB_N;
+      const int par = it & 1;
+      {
+        const size_t gi = ((size_t)s_idx * p.H + h) * ATB_N + tid;
+        reinterpret_cast<float*>(smem + L::OFF_LSE)[par * 256 + tid] = -p.lse2[gi];
+        reinterpret_cast<float*>(smem + L::OFF_DELTA)[par * 256 + tid] = -p.delta[gi] * p.scale;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll 1
+      for (int s = g; s < 8; s += 2) {
+        const int j = s >> 2, qs = s & 3;
+        const uint32_t tS = tmem_base + g * 128 + lane_sel;
+        mbar_wait(&bar_free[qs], j ^ 1);              // the dQ / dK MMAs that read this dS^T sub-block have retired
+        mbar_wait(&bar_s[g], (s >> 1) & 1);
+        tc_fence_after();
+        const uint32_t ds_row = sDS + qs * 16384 + r * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {        // 32 queries at a time
+          uint32_t rs[32], rd[32];
+          tmem_ld_32x32(tS + half * 32, rs);
+          tmem_ld_32x32(tS + 64 + half * 32, rd);
+          const uint32_t qoff = (uint32_t)(par * 256 + qs * 64 + half * 32) * 4;
+          float4 nl[8], nd[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            nl[e] = lds128_b(sLse + qoff + e * 16);
+            nd[e] = lds128_b(sDel + qoff + e * 16);
+          }
+          tmem_wait_ld();
+          uint32_t pp[16], dd[16];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            // P^T = exp2(S^T c - lse2[q]);  dS^T = P^T (dP^T scale - delta[q] scale)
+            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(rs[4 * e]), __uint_as_float(rs[4 * e + 1])), c2,
+                                         make_float2(nl[e].x, nl[e].y));
+            const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(rs[4 * e + 2]), __uint_as_float(rs[4 * e + 3])), c2,
+                                         make_float2(nl[e].z, nl[e].w));
+            const float2 p0 = make_float2(ex2_approx_b(x0.x), ex2_approx_b(x0.y));
+            const float2 p1 = make_float2(ex2_approx_b(x1.x), ex2_approx_b(x1.y));
+            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(rd[4 * e]), __uint_as_float(rd[4 * e + 1])), sc2,
+                                         make_float2(nd[e].x, nd[e].y));
+            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(rd[4 * e + 2]), __uint_as_float(rd[4 * e + 3])), sc2,
+                                         make_float2(nd[e].z, nd[e].w));
+            const float2 d0 = __fmul2_rn(p0, t0), d1 = __fmul2_rn(p1, t1);
+            pp[2 * e] = pack_bf16x2(p0.x, p0.y);
+            pp[2 * e + 1] = pack_bf16x2(p1.x, p1.y);
+            dd[2 * e] = pack_bf16x2(d0.x, d0.y);
+            dd[2 * e + 1] = pack_bf16x2(d1.x, d1.y);
+          }
+          // P^T -> TMEM (bf16 pairs: 32 queries = 16 columns); the S^T columns it lands on were read in an earlier half
+          // or just above (half 0 writes cols [0,16), read range of half 1 is [32,64))
+          tmem_st_32x16(tS + half * 16, pp);
+          // dS^T -> shared memory: row = key r, 16-byte chunk (8 queries) index ^ (r & 7)
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4)
+            sts128_b(ds_row + (uint32_t)(((half * 4 + v4) ^ (r & 7)) * 16), dd[4 * v4], dd[4 * v4 + 1], dd[4 * v4 + 2], dd[4 * v4 + 3]);
+        }
+        tmem_wait_st();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bar_pd[g]);
+        if (qs >= 2) {
+          // last sub-tile of this warpgroup in key tile j: once the tile's MMAs retired, write dK_j (warpgroup 0) /
+          // dV_j (warpgroup 1); after the second key tile also dQ_0 / dQ_1
+          mbar_wait(bar_acc, j);
+          tc_fence_after();
+          bf16* drow = p.dqkv + ((size_t)row0 + j * 128 + r) * (3 * p.E) + h * ATB_D;
+          if (g == 0) store_tmem_row64(tDK + lane_sel, drow + p.E);
+          else        store_tmem_row64(tDV + lane_sel, drow + 2 * p.E);
+          if (j == 1) {
+            bf16* qrow = p.dqkv + ((size_t)row0 + g * 128 + r) * (3 * p.E) + h * ATB_D;
+            store_tmem_row64(tDQ + g * 64 + lane_sel, qrow);
+          }
+          tc_fence_before();
+          mbar_arrive(bar_epi);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int g_mhsa_bwd_variant = 1;   // 1 = pipelined persistent kernel (default), 0 = one CTA per (sequence, head)
+
 }  // namespace ccd
 
 using namespace ccd;
@@ -301,8 +567,31 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
   }
   mhsa_delta_kernel<<<(S * ATB_N + 7) / 8, 256, 0, stream>>>(p.o, p.d_o, delta_ws, S * ATB_N, E, H);
   CCD_LAUNCH_CHECK();
+  if (g_mhsa_bwd_variant == 1) {
+    static bool attr2_set = false;
+    static int num_sms = 148;
+    if (!attr2_set) {
+      CCD_CUDA_CHECK(cudaFuncSetAttribute(mhsa_bwd_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          MhsaBwd2Smem::SMEM_BYTES));
+      int dev = 0;
+      CCD_CUDA_CHECK(cudaGetDevice(&dev));
+      CCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+      attr2_set = true;
+    }
+    const int n_items = S * H;
+    mhsa_bwd_pipelined_kernel<<<n_items < num_sms ? n_items : num_sms, ATB_THREADS, MhsaBwd2Smem::SMEM_BYTES, stream>>>(
+        tmQKV, tmDO, p, n_items);
+    CCD_LAUNCH_CHECK();
+    return CCD_OK;
+  }
   dim3 grid(H, S);
   mhsa_bwd_kernel<<<grid, ATB_THREADS, MhsaBwdSmem::SMEM_BYTES, stream>>>(tmQKV, tmDO, p);
   CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+// debug / A-B switch for the attention backward: 1 = pipelined persistent kernel (default), 0 = first version
+extern "C" int ccd_set_mhsa_bwd_variant(int value) {
+  g_mhsa_bwd_variant = value ? 1 : 0;
   return CCD_OK;
 }

@@ -304,34 +304,51 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+      // Issue order (software pipelined across items so that the two softmax warpgroups run half an item out of phase and
+      // the MUFU never idles while a tile waits for its MMAs):   S0(0) | S1(i)  O0(i)  S0(i+1)  O1(i) | ...
+      // S_t(i+1) overwrites the TMEM columns of P_t(i) / O_t(i): it is issued after O_t(i) (MMAs retire in issue order)
+      // and after the epilogue of tile t has read O_t(i) out (tmem_free[t]).
+      auto issue_s = [&](int t, uint32_t buf) {
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_ss(tmem_base + t * 256, umma_smem_desc_sw128(buf + t * 16384 + k * 32, 16, 1024),
+                  umma_smem_desc_sw128(buf + 32768 + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_o = [&](int t, uint32_t buf) {
+#pragma unroll
+        for (int k = 0; k < ATT_N / 16; ++k)
+          umma_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8,
+                  umma_smem_desc_sw128(buf + 65536 + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(&o_full[t]);
+      };
       int it = 0;
+      if (blockIdx.x < n_items) {
+        mbar_wait(&full_qk[0], 0);
+        tc_fence_after();
+        issue_s(0, smem_u32(smem));
+      }
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int b = it & 1;
         const uint32_t kph = (it >> 1) & 1, ph = it & 1;
         const uint32_t buf = smem_u32(smem + b * ATT2_BUF);
-        mbar_wait(&full_qk[b], kph);
+        mbar_wait(&tmem_free[1], ph ^ 1);         // previous item's O_1 has been read out of TMEM
         tc_fence_after();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&tmem_free[t], ph ^ 1);       // previous item's O_t has been read out of TMEM
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k)
-            umma_ss(tmem_base + t * 256, umma_smem_desc_sw128(buf + t * 16384 + k * 32, 16, 1024),
-                    umma_smem_desc_sw128(buf + 32768 + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&s_full[t]);
-        }
+        issue_s(1, buf);
         mbar_wait(&full_v[b], kph);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], ph);
+        mbar_wait(&p_full[0], ph);
+        tc_fence_after();
+        issue_o(0, buf);
+        if (w + (int)gridDim.x < n_items) {       // S_0 of the next item (other Q/K/V buffer)
+          const int it1 = it + 1;
+          mbar_wait(&full_qk[it1 & 1], (it1 >> 1) & 1);
+          mbar_wait(&tmem_free[0], (it1 & 1) ^ 1);
           tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < ATT_N / 16; ++k)
-            umma_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8,
-                    umma_smem_desc_sw128(buf + 65536 + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
-          umma_commit(&o_full[t]);
+          issue_s(0, smem_u32(smem + (it1 & 1) * ATT2_BUF));
         }
+        mbar_wait(&p_full[1], ph);
+        tc_fence_after();
+        issue_o(1, buf);
         umma_commit(&empty[b]);                   // Q/K/V buffer reusable once every MMA of this item retired
       }
     }
@@ -366,7 +383,10 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
         mx = fmaxf(mx, fmaxf(m0, m1));
       }
       const float mc = mx * c;
-      float sum0 = 0.f, sum1 = 0.f;
+      // packed fp32x2 scale and sum (FFMA2 / FADD2): 5 issue slots per pair of scores instead of 9.  The normaliser sums
+      // the unrounded probabilities (what the saved log-sum-exp must describe for the backward's recomputation of P).
+      const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+      float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int ch = 0; ch < ATT_N / 64; ++ch) {
         uint32_t ra[32], rb[32];
@@ -376,18 +396,19 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
         uint32_t pa[16], pb[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float a0 = ex2_approx(fmaf(__uint_as_float(ra[2 * j]), c, -mc));
-          const float a1 = ex2_approx(fmaf(__uint_as_float(ra[2 * j + 1]), c, -mc));
-          const float b0 = ex2_approx(fmaf(__uint_as_float(rb[2 * j]), c, -mc));
-          const float b1 = ex2_approx(fmaf(__uint_as_float(rb[2 * j + 1]), c, -mc));
-          pa[j] = pack_bf16x2(a0, a1);
-          pb[j] = pack_bf16x2(b0, b1);
-          sum0 += bf16lo(pa[j]) + bf16hi(pa[j]);    // the rounded values: P V / sum(P) stays a convex combination
-          sum1 += bf16lo(pb[j]) + bf16hi(pb[j]);
+          const float2 xa = __ffma2_rn(make_float2(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1])), c2, nmc2);
+          const float2 xb = __ffma2_rn(make_float2(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1])), c2, nmc2);
+          const float2 ea = make_float2(ex2_approx(xa.x), ex2_approx(xa.y));
+          const float2 eb = make_float2(ex2_approx(xb.x), ex2_approx(xb.y));
+          pa[j] = pack_bf16x2(ea.x, ea.y);
+          pb[j] = pack_bf16x2(eb.x, eb.y);
+          sa = __fadd2_rn(sa, ea);
+          sb = __fadd2_rn(sb, eb);
         }
         tmem_st_32x16(tS + lane_sel + ch * 32, pa);        // P chunk (bf16 pairs) over S columns already consumed
         tmem_st_32x16(tS + lane_sel + ch * 32 + 16, pb);
       }
+      const float sum0 = sa.x + sa.y, sum1 = sb.x + sb.y;
       const float sum = sum0 + sum1;
       tmem_wait_st();
       tc_fence_before();

@@ -114,6 +114,8 @@ class VisionTransformer(nn.Module):
         self.register_buffer("_pos_w", pos_resample_matrix(), persistent=False)
         self._cast = ops.ChunkTable()
         self._bf16 = None
+        self._bf16_ver = None
+        self._keep = None
 
     # ---- flat parameter list handed to the autograd.Function (fixed order) ----
     def _param_list(self):
@@ -126,16 +128,36 @@ class VisionTransformer(nn.Module):
             ps += [ln.weight, ln.bias]
         return ps
 
-    def _bf16_weights(self):
-        """bf16 operand copies of the GEMM weights: one multi-tensor cast kernel per forward."""
+    def _bf16_srcs(self):
         srcs = []
         for blk in self.blocks:
             sd = dict(blk.named_parameters())
-            srcs += [sd[k].detach() for k in _GEMM_W]
+            srcs += [sd[k] for k in _GEMM_W]
+        return srcs
+
+    def bf16_copies(self):
+        """(parameter, bf16 operand copy) pairs, for the fused optimizer step that refreshes the copies in its own pass."""
+        return list(zip(self._bf16_srcs(), self._bf16)) if self._bf16 is not None else []
+
+    def bf16_mark_fresh(self):
+        self._bf16_ver = tuple(p._version for p in self._bf16_srcs())
+
+    def bf16_is_fresh(self):
+        return self._bf16_ver == tuple(p._version for p in self._bf16_srcs())
+
+    def _bf16_weights(self):
+        """bf16 operand copies of the GEMM weights: one multi-tensor cast kernel, skipped while the copies are fresh
+        (tensor version counters unchanged since the cast / since the fused optimizer step rewrote them)."""
+        params = self._bf16_srcs()
+        srcs = [p.detach() for p in params]
         if self._bf16 is None or self._bf16[0].device != srcs[0].device:
             self._bf16 = [torch.empty(s.shape, dtype=torch.bfloat16, device=s.device) for s in srcs]
-        table, n = self._cast.get(srcs, self._bf16, 2)
-        ops.multi_tensor(ops.MT_CAST_BF16, table, n)
+            self._bf16_ver = None
+        ver = tuple(p._version for p in params)
+        if ver != self._bf16_ver:
+            table, n = self._cast.get(srcs, self._bf16, 2)
+            ops.multi_tensor(ops.MT_CAST_BF16, table, n)
+            self._bf16_ver = ver
         E = self.embed_dim
         wp = torch.zeros(E, 64, dtype=torch.bfloat16, device=srcs[0].device)     # K padded 48 -> 64
         wp[:, :48] = self.patch_embed.proj.weight.detach().reshape(E, 48)
@@ -147,7 +169,10 @@ class VisionTransformer(nn.Module):
         drop = None
         if self.training and any(b.drop_prob > 0 for b in self.blocks):
             n = x.shape[0]
-            keep = torch.tensor([1.0 - b.drop_prob for b in self.blocks for _ in range(2)], device=x.device).view(-1, 1)
+            keep = self._keep
+            if keep is None or keep.device != x.device:       # constant of the architecture: uploaded once (a pageable
+                keep = self._keep = torch.tensor(             # H2D copy per forward would stall the host on the stream)
+                    [1.0 - b.drop_prob for b in self.blocks for _ in range(2)], device=x.device).view(-1, 1)
             # drop_path (vision_transformer.py:27-36): floor(keep + U[0,1)) / keep per sample, separately per branch
             drop = (torch.floor(keep + torch.rand(2 * len(self.blocks), n, device=x.device)) / keep).contiguous()
         wp, wb = self._bf16_weights()

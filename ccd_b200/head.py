@@ -45,15 +45,33 @@ class DINOHead(nn.Module):
             self.last_layer.weight_g.requires_grad = False
         self._cast = ops.ChunkTable()
         self._bf16 = None
+        self._bf16_ver = None
         self._wn = None
 
+    def _bf16_srcs(self):
+        return [self.mlp[0].weight, self.mlp[2].weight, self.mlp[4].weight]
+
+    def bf16_copies(self):
+        return list(zip(self._bf16_srcs(), self._bf16)) if self._bf16 is not None else []
+
+    def bf16_mark_fresh(self):
+        self._bf16_ver = tuple(p._version for p in self._bf16_srcs())
+
+    def bf16_is_fresh(self):
+        return self._bf16_ver == tuple(p._version for p in self._bf16_srcs())
+
     def _bf16_weights(self):
-        srcs = [self.mlp[0].weight.detach(), self.mlp[2].weight.detach(), self.mlp[4].weight.detach()]
+        params = self._bf16_srcs()
+        srcs = [p.detach() for p in params]
         if self._bf16 is None or self._bf16[0].device != srcs[0].device:
             self._bf16 = [torch.empty(s.shape, dtype=torch.bfloat16, device=s.device) for s in srcs]
             self._wn = torch.empty(self.last_layer.weight_v.shape, dtype=torch.bfloat16, device=srcs[0].device)
-        table, n = self._cast.get(srcs, self._bf16, 2)
-        ops.multi_tensor(ops.MT_CAST_BF16, table, n)
+            self._bf16_ver = None
+        ver = tuple(p._version for p in params)
+        if ver != self._bf16_ver:             # skipped while fresh (see VisionTransformer._bf16_weights)
+            table, n = self._cast.get(srcs, self._bf16, 2)
+            ops.multi_tensor(ops.MT_CAST_BF16, table, n)
+            self._bf16_ver = ver
         return self._bf16
 
     def forward(self, x):

@@ -11,9 +11,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO_PATH = os.path.join(HERE, "libccd_b200.so")
+SO_PATH = os.environ.get("CCD_LIB", os.path.join(HERE, "libccd_b200.so"))   # CCD_LIB: experiment builds (tools/)
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ccd_b200.h")
-SOURCES = ["gemm_umma.cu", "mhsa_fwd.cu", "mhsa_bwd.cu", "rowwise.cu", "dino_loss.cu", "charseg.cu", "seghead.cu", "abi.cu"]
+SOURCES = ["gemm_umma.cu", "mhsa_fwd.cu", "mhsa_bwd.cu", "rowwise.cu", "dino_loss.cu", "charseg.cu", "seghead.cu", "optim.cu", "abi.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
@@ -34,29 +34,31 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into ccd_b200/libccd_b200.so (cross-compiles without a GPU)."""
-    if not force and not _stale():
-        return SO_PATH
+def build(force=False, verbose=False, defines=(), out=None, tag=""):
+    """Compile every CUDA source for sm_100a into ccd_b200/libccd_b200.so (cross-compiles without a GPU).
+    `defines` / `out` / `tag`: experiment builds with extra -D switches into another .so (tools/build_variants.py)."""
+    out = out or SO_PATH
+    if not force and not defines and not _stale():
+        return out
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(HERE, "build", src.replace(".cu", tag + ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-        if verbose and out.strip():
-            print(out)
-    cmd = [_nvcc(), "-shared", "-o", SO_PATH, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+            raise RuntimeError(f"nvcc failed on {src}:\n{log}")
+        if verbose and log.strip():
+            print(log)
+    cmd = [_nvcc(), "-shared", "-o", out, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    return SO_PATH
+    return out
 
 
 def declared_symbols():

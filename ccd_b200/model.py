@@ -17,14 +17,43 @@ from . import ops
 SLOTS = 26
 
 
+class _RowCount:
+    """The single device->host read of the step: R = offs[-1], the ragged row count that fixes the [2R,K] output shape.
+    The 4-byte copy into pinned memory is queued right behind the plan kernels; the host only waits for it when the
+    value is first needed (CharPoolFn.forward), i.e. after the whole encoder forward has been enqueued, so neither the
+    host nor the GPU idles on the round trip."""
+    _ring, _next = [], 0
+
+    def __init__(self, offs):
+        cls = _RowCount
+        if len(cls._ring) < 8:
+            cls._ring.append(torch.empty(1, dtype=torch.int32).pin_memory())
+        self.host = cls._ring[cls._next % len(cls._ring)]
+        cls._next += 1
+        self.host.copy_(offs[-1:], non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+        self.value = None
+
+    def get(self):
+        if self.value is None:
+            self.event.synchronize()
+            self.value = int(self.host[0])
+        return self.value
+
+
 class ClusterMaps:
     """What `student_output['zero']` holds: per-pixel slot bitmasks of both views + the pooling plan.
     train.py:233 passes it straight to the teacher (`clusters=student_output['zero']`)."""
 
     def __init__(self, bits, tot4, cnt, offs, new_index_u8, R, ready_event=None):
-        self.bits, self.tot4, self.cnt, self.offs, self.new_index_u8, self.R = bits, tot4, cnt, offs, new_index_u8, R
+        self.bits, self.tot4, self.cnt, self.offs, self.new_index_u8, self._R = bits, tot4, cnt, offs, new_index_u8, R
         self.ready_event = ready_event
         self._dense = None
+
+    @property
+    def R(self):
+        return self._R.get() if isinstance(self._R, _RowCount) else self._R
 
     @property
     def shape(self):
@@ -40,8 +69,7 @@ class ClusterMaps:
     def from_dense(dense):
         bits = ops.dense_to_bits(dense.contiguous().float())
         tot4, cnt, offs, new_index = ops.char_plan(bits)
-        R = int(offs[-1].item())
-        return ClusterMaps(bits, tot4, cnt, offs, new_index, R)
+        return ClusterMaps(bits, tot4, cnt, offs, new_index, _RowCount(offs))
 
 
 class CharPoolFn(torch.autograd.Function):
@@ -97,9 +125,7 @@ class ABIDINOModel(nn.Module):
         bits2 = ops.warp_bits(bits1, metrics.contiguous().float())
         bits = torch.cat([bits1, bits2])
         tot4, cnt, offs, new_index = ops.char_plan(bits)
-        # the single device->host read of the step: the row count that fixes the [2R,K] output shape
-        R = int(offs[-1].item())
-        return ClusterMaps(bits, tot4, cnt, offs, new_index, R)
+        return ClusterMaps(bits, tot4, cnt, offs, new_index, _RowCount(offs))     # R is read lazily (see _RowCount)
 
     def forward(self, x, metrics, target_mask, epoch, clusters=None, index=None):
         if not x.is_cuda:

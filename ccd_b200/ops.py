@@ -46,6 +46,8 @@ def _bind():
     import os
     if "CCD_GEMM_VARIANT" in os.environ:            # debug A/B switch (1 = persistent [default], 0 = one tile per CTA)
         _FN["ccd_set_option"](0, int(os.environ["CCD_GEMM_VARIANT"]))
+    if "CCD_MHSA_BWD_VARIANT" in os.environ:        # 1 = pipelined persistent [default], 0 = first version
+        _FN["ccd_set_mhsa_bwd_variant"](int(os.environ["CCD_MHSA_BWD_VARIANT"]))
 
 
 def _call(name, *args, work=None):
@@ -149,6 +151,12 @@ def mhsa_bwd(qkv, o, d_o, lse, S, H):
     return dqkv
 
 
+def set_mhsa_bwd_variant(v):
+    """1 = pipelined persistent backward kernel (default), 0 = first version (A/B switch, see include/ccd_b200.h)."""
+    _bind()
+    _FN["ccd_set_mhsa_bwd_variant"](int(v))
+
+
 def layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=False):
     rows, E = x.shape
     yb = torch.empty(rows, E, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
@@ -216,43 +224,61 @@ def cast_bf16(src, dst=None):
     return dst
 
 
+def _upload_table(rows, dev):
+    """Pointer table -> device without a host stall: pinned staging + asynchronous copy (a pageable torch.tensor(...).to(dev)
+    is a synchronous cudaMemcpy that waits for everything queued on the stream)."""
+    host = torch.tensor(rows, dtype=torch.int64)
+    if torch.device(dev).type != "cuda":          # host-logic unit tests only; every kernel call refuses CPU tensors
+        return host, host
+    host = host.pin_memory()
+    t = host.to(dev, non_blocking=True)
+    return t, host          # the pinned buffer must outlive the copy: the caller keeps it
+
+
 class ChunkTable:
-    """Device pointer table for the multi-tensor kernels; rebuilt only when a data_ptr changes."""
+    """Device pointer table for the multi-tensor kernels; built once per distinct set of data_ptrs (cached)."""
     CHUNK = 1 << 16
 
     def __init__(self):
-        self.key = None
-        self.table = None
-        self.n = 0
+        self.cache = {}
 
     def get(self, srcs, dsts, dst_itemsize):
         key = tuple(t.data_ptr() for t in srcs) + tuple(t.data_ptr() for t in dsts)
-        if key != self.key:
+        hit = self.cache.get(key)
+        if hit is None:
             rows = []
             for s, d in zip(srcs, dsts):
                 assert s.is_contiguous() and d.is_contiguous() and s.numel() == d.numel()
                 n = s.numel()
                 for o in range(0, n, self.CHUNK):
                     rows.append((s.data_ptr() + 4 * o, d.data_ptr() + dst_itemsize * o, min(self.CHUNK, n - o)))
-            self.table = torch.tensor(rows, dtype=torch.int64).to(srcs[0].device)
-            self.n = len(rows)
-            self.key = key
-        return self.table, self.n
+            if len(self.cache) >= 8:
+                self.cache.clear()
+            hit = self.cache[key] = (*_upload_table(rows, srcs[0].device), len(rows))
+        return hit[0], hit[2]
+
+
+class _ClipEntry:
+    pass
 
 
 class ClipTable:
-    """Pointer tables for the multi-tensor per-parameter clip: (grad chunk -> &sqnorm[i]) and (&sqnorm[i] -> grad chunk)."""
+    """Pointer tables for the multi-tensor per-parameter clip: (grad chunk -> &sqnorm[i]) and (&sqnorm[i] -> grad chunk).
+    Gradient buffers are re-allocated every step (zero_grad(set_to_none=True)) and the caching allocator alternates
+    between a few addresses: the tables are cached per address set instead of being rebuilt (and re-uploaded) per step."""
     CHUNK = 1 << 16
 
     def __init__(self):
-        self.key = None
+        self.cache = {}
 
     def get(self, grads):
         key = tuple(g.data_ptr() for g in grads)
-        if key != self.key:
+        e = self.cache.get(key)
+        if e is None:
             dev = grads[0].device
-            self.norms = torch.zeros(len(grads), dtype=torch.float32, device=dev)
-            base = self.norms.data_ptr()
+            e = _ClipEntry()
+            e.norms = torch.zeros(len(grads), dtype=torch.float32, device=dev)
+            base = e.norms.data_ptr()
             a, b = [], []
             for i, g in enumerate(grads):
                 assert g.is_contiguous() and g.dtype == torch.float32
@@ -260,11 +286,13 @@ class ClipTable:
                     n = min(self.CHUNK, g.numel() - o)
                     a.append((g.data_ptr() + 4 * o, base + 4 * i, n))
                     b.append((base + 4 * i, g.data_ptr() + 4 * o, n))
-            self.t_norm = torch.tensor(a, dtype=torch.int64).to(dev)
-            self.t_clip = torch.tensor(b, dtype=torch.int64).to(dev)
-            self.n = len(a)
-            self.key = key
-        return self
+            e.t_norm, e._h0 = _upload_table(a, dev)
+            e.t_clip, e._h1 = _upload_table(b, dev)
+            e.n = len(a)
+            if len(self.cache) >= 8:
+                self.cache.clear()
+            self.cache[key] = e
+        return e
 
 
 def clip_per_parameter_(grads, clip, table):
@@ -278,6 +306,16 @@ def clip_per_parameter_(grads, clip, table):
 
 def multi_tensor(op, table, n, a=0.0, b=0.0):
     _call("ccd_multi_tensor", op, _p(table), n, float(a), float(b), _s())
+
+
+def fused_adamw(table, grad_ptrs, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, clip, ema_m):
+    """Per-parameter clip + AdamW + teacher EMA + bf16 operand refresh in one pass.  See include/ccd_b200.h:ccd_fused_adamw."""
+    _call("ccd_fused_adamw", _p(table), _p(grad_ptrs), n, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+          float(bc1), float(bc2), float(clip), float(ema_m), _s())
+
+
+def grad_sqnorm(table, grad_ptrs, n):
+    _call("ccd_grad_sqnorm", _p(table), _p(grad_ptrs), n, _s())
 
 
 def patch_im2col(x_img):

@@ -69,6 +69,9 @@ class TeacherEMA:
         self.pairs = list(zip(student.backbone.parameters(), teacher.backbone.parameters())) + \
             list(zip(student.head.parameters(), teacher.head.parameters()))
         self.table = ops.ChunkTable()
+        # modules holding bf16 GEMM-operand copies of parameters (refreshed by the fused optimizer step, optim.AdamW)
+        self.bf16_modules = [m for m in (student.backbone, student.head, teacher.backbone, teacher.head)
+                             if hasattr(m, "bf16_copies")]
 
     @torch.no_grad()
     def step(self, m):
@@ -76,3 +79,4 @@ class TeacherEMA:
         dsts = [t.detach() for _, t in self.pairs]
         table, n = self.table.get(srcs, dsts, 4)
         ops.multi_tensor(ops.MT_EMA, table, n, float(m), float(1.0 - m))
+        torch.autograd.graph.increment_version(dsts)      # raw-pointer in-place update: keep version counters honest

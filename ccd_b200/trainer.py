@@ -54,7 +54,14 @@ class PretrainStep:
         for p in teacher.parameters():
             p.requires_grad = False
         self.loss = DINOLoss(out_dim, 2, 0.04, 0.04, 0, 101).to(self.device)                                  # :122-129
-        self.opt = torch.optim.AdamW(get_params_groups(student), fused=True)                                  # :131-133
+        # train.py:131-133 builds torch.optim.AdamW(params_groups); optim.AdamW is the same optimizer whose step() also
+        # folds in the clip (:249), the EMA loop (:264-272) and the bf16 operand refresh (CCD_FUSED_OPT=0: separate calls)
+        self.fused_opt = os.environ.get("CCD_FUSED_OPT", "1") == "1"
+        if self.fused_opt:
+            from .optim import AdamW
+            self.opt = AdamW(get_params_groups(student))
+        else:
+            self.opt = torch.optim.AdamW(get_params_groups(student), fused=True)
         glob = batch_per_gpu * self.world
         self.lr_sched = cosine_iter_scheduler(lr * glob / 256., 1e-6, total_iters,
                                               warmup_iters=min(total_iters // 10, max(1, int(10 * 1000000 / glob))))
@@ -87,11 +94,15 @@ class PretrainStep:
             self._loss_event.record()
         self.opt.zero_grad(set_to_none=True)                                                                  # :244
         loss.backward()                                                                                       # :247
-        if self.clip_grad:
-            clip_gradients(self.student, self.clip_grad)                                                      # :249
-        cancel_gradients_last_layer(epoch, self.student, self.freeze_last_layer)                              # :250
-        self.opt.step()                                                                                       # :252
-        self.ema.step(float(self.mom_sched[it]))                                                              # :264-272
+        if self.fused_opt:
+            cancel_gradients_last_layer(epoch, self.student, self.freeze_last_layer)                          # :250
+            self.opt.step(clip_grad=self.clip_grad, ema=self.ema, ema_momentum=float(self.mom_sched[it]))     # :249,252,264-272
+        else:
+            if self.clip_grad:
+                clip_gradients(self.student, self.clip_grad)                                                  # :249
+            cancel_gradients_last_layer(epoch, self.student, self.freeze_last_layer)                          # :250
+            self.opt.step()                                                                                   # :252
+            self.ema.step(float(self.mom_sched[it]))                                                          # :264-272
         self.iteration += 1
         if sync_loss:
             self._loss_event.synchronize()

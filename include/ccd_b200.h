@@ -48,6 +48,8 @@ int ccd_mhsa_fwd(const void* qkv, void* out, float* lse2, int S, int H, int vari
  * small pre-pass).  Replaces autograd of vision_transformer.py:85-89. */
 int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, float* delta_ws, void* dqkv, int S, int H,
                  void* stream);
+/* A/B switch (debug): 1 = pipelined persistent backward kernel (default), 0 = first version (one CTA per (sequence, head)) */
+int ccd_set_mhsa_bwd_variant(int value);
 
 /* LayerNorm (eps 1e-6) over f32 rows -> bf16 and/or f32.  Block.norm1/norm2, norm, norm_seg: vision_transformer.py:108-110,247,250 */
 int ccd_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, int rows, int E,
@@ -75,6 +77,17 @@ int ccd_weightnorm_bwd(const float* dw, const float* v, const float* g, const fl
  * op 3: *dst += sum(src^2) ; op 4: dst *= a/(sqrt(*src)+1e-6) if < 1  (per-parameter clip, Dino/modules/utils.py:132-141) */
 int ccd_multi_tensor(int op, const void* table_dev, int n_chunks, float a, float b, void* stream);
 int ccd_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* Fused optimizer step over a device table int64[n_chunks][10] =
+ *   (param, grad_ref, exp_avg, exp_avg_sq, sqnorm_ptr|0, ema_dst|0, param_bf16|0, ema_bf16|0, n_elems, flags);
+ *   grad_ref = tensor_index | (element_offset << 16) into grad_ptrs_dev (int64[n_tensors], refreshed per step):
+ *   g' = g * min(1, clip/(sqrt(*sqnorm)+1e-6))      per-parameter clip, Dino/modules/utils.py:132-141 (clip <= 0 or ptr 0: off)
+ *   AdamW (torch.optim.AdamW as train.py:131-133,252 drives it): p *= 1-lr*wd (flags&1); m,v moments; p -= lr/bc1 * m/(sqrt(v)/sqrt(bc2)+eps)
+ *   ema_dst = ema_m*ema_dst + (1-ema_m)*p            teacher EMA, train.py:264-272   (flags&2: EMA only, no AdamW update)
+ *   param_bf16 / ema_bf16 = bf16 copies of the updated values (the GEMM operand copies of the next forward).
+ * ccd_grad_sqnorm: *sqnorm_ptr += sum(g^2) per row of the same table (caller zero-fills the norms). */
+int ccd_grad_sqnorm(const void* table_dev, const void* grad_ptrs_dev, int n_chunks, void* stream);
+int ccd_fused_adamw(const void* table_dev, const void* grad_ptrs_dev, int n_chunks, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float bias_correction1, float bias_correction2, float clip, float ema_m, void* stream);
 /* center = center*m + (sum/denom)*(1-m)   (DINOLoss.update_center, Dino/loss/Dino_loss.py:140-143) */
 int ccd_center_ema(float* center, const float* sum, float denom, float momentum, int n, void* stream);
 /* x f32 [N,3,32,128] -> bf16 [N*256, 64] patch columns (k = c*16+ky*4+kx, zero padded 48..63) */

@@ -133,13 +133,19 @@ def test_mhsa_fwd(ops, variant, S, H):
     assert (lse.double() - rl).abs().max() < 2e-2
 
 
-@pytest.mark.parametrize("S,H", [(2, 3), (3, 8)])
-def test_mhsa_bwd(ops, S, H):
+@pytest.mark.parametrize("variant", [1, 0])           # 1 = pipelined persistent kernel (default), 0 = first version
+@pytest.mark.parametrize("S,H", [(2, 3), (3, 8), (70, 6)])   # 420 items > 148 SMs: several items per persistent CTA
+def test_mhsa_bwd(ops, S, H, variant):
     g = torch.Generator(device="cuda").manual_seed(S + H)
     qkv = _bf(torch.randn(S * 256, 3 * H * 64, device="cuda", generator=g))
     d_o = _bf(torch.randn(S * 256, H * 64, device="cuda", generator=g))
     o, lse = ops.mhsa_fwd(qkv, S, H, True, 0)
-    dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, S, H)
+    ops.set_mhsa_bwd_variant(variant)
+    try:
+        dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, S, H)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_mhsa_bwd_variant(1)
     x = qkv.double().requires_grad_(True)
     ro, _, _ = _attn_ref(x, S, H)
     (ro * d_o.double()).sum().backward()
@@ -386,3 +392,100 @@ def test_multi_tensor_clip(ops):
     for (n, p), n0, n1 in zip(lin.named_parameters(), norms0, norms.tolist()):
         assert abs(n0 - n1) < 1e-3 * n0
         assert (p.grad - want[n]).abs().max() < 1e-5 * max(1.0, want[n].abs().max().item())
+
+
+def test_fused_adamw_clip_ema(ops):
+    """optim.AdamW.step(clip_grad, ema) == clip_gradients (oracle) -> torch.optim.AdamW -> EMA, incl. parameters that skip a
+    step (frozen last layer: different step counts), a weight-decay-free group, EMA-only pairs and bf16 copies."""
+    import ccd_oracle as O
+    from ccd_b200.optim import AdamW
+
+    class Holder:            # stands in for TeacherEMA + the modules that own bf16 operand copies
+        pass
+
+    g = torch.Generator(device="cuda").manual_seed(21)
+    shapes = [(300, 130), (70001,), (384, 1152), (2,), (17, 3)]
+    mine = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+    frozen = torch.nn.Parameter(torch.randn(33, device="cuda", generator=g), requires_grad=False)   # EMA only (weight_g)
+    teach = [torch.randn(s, device="cuda", generator=g) for s in shapes] + [torch.randn(33, device="cuda", generator=g)]
+    teach_ref = [t.clone() for t in teach]
+    bf_s = torch.empty(shapes[2], dtype=torch.bfloat16, device="cuda")
+    bf_t = torch.empty(shapes[2], dtype=torch.bfloat16, device="cuda")
+
+    class Mod:
+        def __init__(self, p, b):
+            self.p, self.b, self.ver = p, b, None
+        def bf16_copies(self):
+            return [(self.p, self.b)]
+        def bf16_is_fresh(self):
+            return True
+        def bf16_mark_fresh(self):
+            self.ver = self.p._version
+
+    ema = Holder()
+    ema.pairs = list(zip(mine + [frozen], teach))
+    ema.bf16_modules = [Mod(mine[2], bf_s), Mod(teach[2], bf_t)]
+    groups = lambda ps: [{"params": [ps[0], ps[2], ps[4]]}, {"params": [ps[1], ps[3]], "weight_decay": 0.0}]
+    opt = AdamW(groups(mine))
+    opt_ref = torch.optim.AdamW(groups(ref))
+    clip, mom = 3.0, 0.99
+    for it in range(4):
+        lr, wd = 1e-3 * (it + 1), 0.04 + 0.01 * it
+        for o in (opt, opt_ref):
+            for i, gr in enumerate(o.param_groups):
+                gr["lr"] = lr
+                if i == 0:
+                    gr["weight_decay"] = wd
+        grads = [torch.randn(s, device="cuda", generator=g) * sc for s, sc in zip(shapes, (0.05, 0.001, 0.5, 3.0, 0.2))]
+        skip = {4} if it == 1 else set()            # parameter 4 has no gradient on step 1 -> its step count lags
+        clipped = O.clip_per_parameter({str(i): gr.clone() for i, gr in enumerate(grads)}, clip)
+        for i, (p, r) in enumerate(zip(mine, ref)):
+            p.grad = None if i in skip else grads[i].clone()
+            r.grad = None if i in skip else clipped[str(i)].clone()
+        opt.step(clip_grad=clip, ema=ema, ema_momentum=mom)
+        opt_ref.step()
+        with torch.no_grad():
+            for t, s in zip(teach_ref, ref + [frozen]):
+                t.mul_(mom).add_((1 - mom) * s.detach())
+        for p, r in zip(mine, ref):
+            assert (p - r).abs().max().item() < 2e-6 * max(1.0, r.abs().max().item())
+        for t, tr in zip(teach, teach_ref):
+            assert (t - tr).abs().max().item() < 2e-6 * max(1.0, tr.abs().max().item())
+        assert torch.equal(bf_s, mine[2].detach().to(torch.bfloat16)) and torch.equal(bf_t, teach[2].to(torch.bfloat16))
+        assert ema.bf16_modules[0].ver == mine[2]._version
+    sd = opt.state_dict()
+    assert torch.is_tensor(sd["state"][0]["step"]) and float(sd["state"][0]["step"]) == 4.0 and float(sd["state"][2]["step"]) == 3.0
+    opt_ref.load_state_dict(sd)                     # interchange with torch.optim.AdamW
+    opt.load_state_dict(opt_ref.state_dict())
+    assert opt.state[mine[4]]["step"] == 3
+
+
+def test_gelu_epilogue_accuracy(ops):
+    """Fused GELU / GELU' epilogues (packed polynomial + MUFU.TANH) against the exact erf form over x in [-12, 12]:
+    absolute error beyond the bf16 rounding of the stored result stays below 1.5e-3 (GELU) / 3e-3 (GELU')."""
+    import json
+    M, N, K = 4096, 256, 64
+    x = torch.linspace(-12.0, 12.0, M, device="cuda").to(torch.bfloat16)
+    A = torch.zeros(M, K, dtype=torch.bfloat16, device="cuda")
+    A[:, 0] = x
+    B = torch.zeros(N, K, dtype=torch.bfloat16, device="cuda")
+    B[:, 0] = 1.0
+    act = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, B, M, N, K, 0, 0, ops.EPI_GELU, None, None, act)
+    xd = x.double()
+    exact = 0.5 * xd * (1.0 + torch.erf(xd / math.sqrt(2.0)))
+    err = (act[:, 0].double() - exact).abs() - exact.abs() * 2.0 ** -8
+    assert torch.equal(act[:, 0], act[:, N - 1])
+    A[:, 0] = 1.0
+    aux = x.view(M, 1).expand(M, N).contiguous()
+    dout = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, B, M, N, K, 0, 0, ops.EPI_DGELU, None, dout, None, aux)
+    dexact = 0.5 * (1.0 + torch.erf(xd / math.sqrt(2.0))) + xd * torch.exp(-0.5 * xd * xd) / math.sqrt(2.0 * math.pi)
+    derr = (dout[:, 0].double() - dexact).abs() - dexact.abs() * 2.0 ** -8
+    rec = {"gelu_max_excess_abs_err": err.max().item(), "gelu_argmax_x": x[err.argmax()].item(),
+           "dgelu_max_excess_abs_err": derr.max().item(), "dgelu_argmax_x": x[derr.argmax()].item()}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/gelu_accuracy.json", "w") as f:
+        json.dump(rec, f)
+    assert err.max().item() < 1.5e-3 and derr.max().item() < 3e-3, rec
