@@ -9,26 +9,34 @@
 
 namespace ccd {
 
-constexpr int BN_ROWS_PER_BLOCK = 128;
+// All four streaming kernels share one shape: blockDim = (C/8 column groups of 8 channels, 256/(C/8) row lanes); a
+// thread keeps the per-channel constants of its 8 channels in registers and walks the rows of its block four at a time
+// (four independent 16-byte loads in flight per operand).  First version: one thread per 16-byte group with ~40 __ldg of
+// per-channel constants each (issue bound, 3.5x off the HBM floor in the step profile) and 128-row blocks (4 M global
+// atomics per statistics pass).
+constexpr int BN_ROWS_PER_BLOCK = 1024;   // statistics kernels: rows per block (global atomics: 2 C per block)
+constexpr int BN_APPLY_ROWS = 256;        // apply kernels: rows per block
 
-// x [M, C] (ld = ldx), C % 8 == 0, C <= 256.  sums[0:C] += sum x, sums[C:2C] += sum x^2   (zero-filled by the caller)
-__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ sums, int M, int C) {
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+  f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
+}
+template <bool F32>
+__device__ __forceinline__ void load_dy8(const void* dy_, size_t off, float (&d)[8]) {
+  if constexpr (F32) {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + off);
+    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + off + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+  } else {
+    unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(dy_) + off), d);
+  }
+}
+// block-level reduction of the per-thread partial sums: shared-memory atomics, then one global atomic per channel
+__device__ __forceinline__ void bn_block_reduce(float (&s)[8], float (&q)[8], float* __restrict__ sums, int C) {
   __shared__ float acc[2][256];
-  const int cg = threadIdx.x;                   // column group of 8 (blockDim = (C/8, 256/(C/8)))
-  const int ty = threadIdx.y, ny = blockDim.y;
+  const int cg = threadIdx.x, ty = threadIdx.y;
   for (int i = ty * blockDim.x + cg; i < 512; i += blockDim.x * blockDim.y) (&acc[0][0])[i] = 0.f;
   __syncthreads();
-  const int r0 = blockIdx.x * BN_ROWS_PER_BLOCK;
-  const int r1 = min(M, r0 + BN_ROWS_PER_BLOCK);
-  float s[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  for (int r = r0 + ty; r < r1; r += ny) {
-    const uint4 v = *reinterpret_cast<const uint4*>(x + (size_t)r * ldx + cg * 8);
-    const float f[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
-  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     atomicAdd(&acc[0][cg * 8 + j], s[j]);
@@ -41,26 +49,67 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
   }
 }
 
-// y[r, yoff + c] = relu((x[r,c] - mean[c]) * rstd[c] * gamma[c] + beta[c])
+// x [M, C] (ld = ldx), C % 8 == 0, C <= 256.  sums[0:C] += sum x, sums[C:2C] += sum x^2   (zero-filled by the caller)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ sums, int M, int C) {
+  const int cg = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  const int r0 = blockIdx.x * BN_ROWS_PER_BLOCK;
+  const int r1 = min(M, r0 + BN_ROWS_PER_BLOCK);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  int r = r0 + ty;
+  for (; r + 3 * ny < r1; r += 4 * ny) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (size_t)(r + u * ny) * ldx + cg * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    }
+  }
+  for (; r < r1; r += ny) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + (size_t)r * ldx + cg * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+  }
+  bn_block_reduce(s, q, sums, C);
+}
+
+// y[r, c] = relu((x[r,c] - mean[c]) * rstd[c] * gamma[c] + beta[c]) = relu(x * sc + sh)
 __global__ void __launch_bounds__(256) bn_apply_relu_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, bf16* __restrict__ y, int ldy, int M, int C) {
-  const int cgs = C >> 3;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)M * cgs) return;
-  const int cg = (int)(idx % cgs);
-  const size_t r = idx / cgs;
-  const uint4 v = *reinterpret_cast<const uint4*>(x + r * ldx + cg * 8);
-  const float f[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
-  float o[8];
+  const int cg = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
-    const float sc = __ldg(rstd + c) * __ldg(gamma + c);
-    o[j] = fmaxf(fmaf(f[j] - __ldg(mean + c), sc, __ldg(beta + c)), 0.f);
+    sc[j] = rstd[c] * gamma[c];
+    sh[j] = fmaf(-mean[c], sc[j], beta[c]);
   }
-  *reinterpret_cast<uint4*>(y + r * ldy + cg * 8) =
-      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  const int r0 = blockIdx.x * BN_APPLY_ROWS;
+  const int r1 = min(M, r0 + BN_APPLY_ROWS);
+  auto one = [&](const uint4& v, int r) {
+    float f[8], o[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+    *reinterpret_cast<uint4*>(y + (size_t)r * ldy + cg * 8) =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  };
+  int r = r0 + ty;
+  for (; r + 3 * ny < r1; r += 4 * ny) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (size_t)(r + u * ny) * ldx + cg * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(v[u], r + u * ny);
+  }
+  for (; r < r1; r += ny) one(*reinterpret_cast<const uint4*>(x + (size_t)r * ldx + cg * 8), r);
 }
 
 // sums[0:C] += sum dz, sums[C:2C] += sum dz * xhat,   dz = dy * [xhat*gamma + beta > 0]
@@ -69,49 +118,48 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const void* __restri
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ sums, int M, int C) {
-  __shared__ float acc[2][256];
   const int cg = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
-  for (int i = ty * blockDim.x + cg; i < 512; i += blockDim.x * blockDim.y) (&acc[0][0])[i] = 0.f;
-  __syncthreads();
   const int r0 = blockIdx.x * BN_ROWS_PER_BLOCK;
   const int r1 = min(M, r0 + BN_ROWS_PER_BLOCK);
-  float s[8], q[8], mu[8], rs[8], ga[8], be[8];
+  // xhat = x * rs - mu * rs ;  y = xhat * gamma + beta = x * ysc + ysh
+  float s[8], q[8], rs[8], mrs[8], ysc[8], ysh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
-    s[j] = 0.f; q[j] = 0.f; mu[j] = mean[c]; rs[j] = rstd[c]; ga[j] = gamma[c]; be[j] = beta[c];
+    s[j] = 0.f; q[j] = 0.f;
+    rs[j] = rstd[c];
+    mrs[j] = -mean[c] * rs[j];
+    ysc[j] = rs[j] * gamma[c];
+    ysh[j] = fmaf(-mean[c], ysc[j], beta[c]);          // same expression as the forward: identical ReLU mask
   }
-  for (int r = r0 + ty; r < r1; r += ny) {
-    const uint4 v = *reinterpret_cast<const uint4*>(x + (size_t)r * ldx + cg * 8);
-    const float f[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
-    float d[8];
-    if constexpr (DY_F32) {
-      const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)r * lddy + cg * 8);
-      const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)r * lddy + cg * 8 + 4);
-      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
-    } else {
-      const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(dy_) + (size_t)r * lddy + cg * 8);
-      d[0] = bf16lo(w.x); d[1] = bf16hi(w.x); d[2] = bf16lo(w.y); d[3] = bf16hi(w.y);
-      d[4] = bf16lo(w.z); d[5] = bf16hi(w.z); d[6] = bf16lo(w.w); d[7] = bf16hi(w.w);
-    }
+  auto one = [&](const uint4& v, const float (&d)[8]) {
+    float f[8];
+    unpack8(v, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (f[j] - mu[j]) * rs[j];
-      const float dz = (fmaf(xh, ga[j], be[j]) > 0.f) ? d[j] : 0.f;
+      const float dz = (fmaf(f[j], ysc[j], ysh[j]) > 0.f) ? d[j] : 0.f;
       s[j] += dz;
-      q[j] += dz * xh;
+      q[j] = fmaf(dz, fmaf(f[j], rs[j], mrs[j]), q[j]);
     }
-  }
+  };
+  int r = r0 + ty;
+  for (; r + ny < r1; r += 2 * ny) {
+    uint4 v[2];
+    float d[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&acc[0][cg * 8 + j], s[j]);
-    atomicAdd(&acc[1][cg * 8 + j], q[j]);
+    for (int u = 0; u < 2; ++u) {
+      v[u] = *reinterpret_cast<const uint4*>(x + (size_t)(r + u * ny) * ldx + cg * 8);
+      load_dy8<DY_F32>(dy_, (size_t)(r + u * ny) * lddy + cg * 8, d[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) one(v[u], d[u]);
   }
-  __syncthreads();
-  for (int i = ty * blockDim.x + cg; i < C; i += blockDim.x * blockDim.y) {
-    atomicAdd(sums + i, acc[0][i]);
-    atomicAdd(sums + C + i, acc[1][i]);
+  for (; r < r1; r += ny) {
+    float d[8];
+    load_dy8<DY_F32>(dy_, (size_t)r * lddy + cg * 8, d);
+    one(*reinterpret_cast<const uint4*>(x + (size_t)r * ldx + cg * 8), d);
   }
+  bn_block_reduce(s, q, sums, C);
 }
 
 // dx = gamma * rstd * (dz - dbeta * inv_m - xhat * dgamma * inv_m)
@@ -121,34 +169,51 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const void* __restric
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ sums, float inv_m, bf16* __restrict__ dx, int lddx,
                                                            int M, int C) {
-  const int cgs = C >> 3;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)M * cgs) return;
-  const int cg = (int)(idx % cgs);
-  const size_t r = idx / cgs;
-  const uint4 v = *reinterpret_cast<const uint4*>(x + r * ldx + cg * 8);
-  const float f[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
-  float d[8];
-  if constexpr (DY_F32) {
-    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + r * lddy + cg * 8);
-    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + r * lddy + cg * 8 + 4);
-    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
-  } else {
-    const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(dy_) + r * lddy + cg * 8);
-    d[0] = bf16lo(w.x); d[1] = bf16hi(w.x); d[2] = bf16lo(w.y); d[3] = bf16hi(w.y);
-    d[4] = bf16lo(w.z); d[5] = bf16hi(w.z); d[6] = bf16lo(w.w); d[7] = bf16hi(w.w);
-  }
-  float o[8];
+  const int cg = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  // dx = a * dz - a * (s1 + xhat * s2) ,  xhat = x * rs + mrs ,  a = gamma * rs  ->  dx = a * dz + x * k1 + k0
+  float a[8], k0[8], k1[8], ysc[8], ysh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
-    const float rs = __ldg(rstd + c), ga = __ldg(gamma + c);
-    const float xh = (f[j] - __ldg(mean + c)) * rs;
-    const float dz = (fmaf(xh, ga, __ldg(beta + c)) > 0.f) ? d[j] : 0.f;
-    o[j] = ga * rs * (dz - __ldg(sums + c) * inv_m - xh * __ldg(sums + C + c) * inv_m);
+    const float rs = rstd[c], ga = gamma[c];
+    const float mrs = -mean[c] * rs;
+    const float s1 = sums[c] * inv_m, s2 = sums[C + c] * inv_m;
+    a[j] = ga * rs;
+    k1[j] = -a[j] * s2 * rs;
+    k0[j] = -a[j] * (s1 + mrs * s2);
+    ysc[j] = rs * ga;
+    ysh[j] = fmaf(-mean[c], ysc[j], beta[c]);          // same expression as the forward: identical ReLU mask
   }
-  *reinterpret_cast<uint4*>(dx + r * lddx + cg * 8) =
-      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  const int r0 = blockIdx.x * BN_APPLY_ROWS;
+  const int r1 = min(M, r0 + BN_APPLY_ROWS);
+  auto one = [&](const uint4& v, const float (&d)[8], int r) {
+    float f[8], o[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dz = (fmaf(f[j], ysc[j], ysh[j]) > 0.f) ? d[j] : 0.f;
+      o[j] = fmaf(a[j], dz, fmaf(f[j], k1[j], k0[j]));
+    }
+    *reinterpret_cast<uint4*>(dx + (size_t)r * lddx + cg * 8) =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  };
+  int r = r0 + ty;
+  for (; r + ny < r1; r += 2 * ny) {
+    uint4 v[2];
+    float d[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      v[u] = *reinterpret_cast<const uint4*>(x + (size_t)(r + u * ny) * ldx + cg * 8);
+      load_dy8<DY_F32>(dy_, (size_t)(r + u * ny) * lddy + cg * 8, d[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) one(v[u], d[u], r + u * ny);
+  }
+  for (; r < r1; r += ny) {
+    float d[8];
+    load_dy8<DY_F32>(dy_, (size_t)r * lddy + cg * 8, d);
+    one(*reinterpret_cast<const uint4*>(x + (size_t)r * ldx + cg * 8), d, r);
+  }
 }
 
 // mean / rstd from the (possibly all-reduced) sums; running statistics with momentum (unbiased variance), as
@@ -180,21 +245,29 @@ constexpr int CLS_ROW_BYTES = (CLS_W + 2) * CLS_PITCH;  // zero pixel on each si
 constexpr int CLS_ROWS_BYTES = 3 * CLS_ROW_BYTES;       // 106080
 constexpr int CLS_WS = CLS_C + 4;
 
-// stage rows y-1, y, y+1 of image n (zeros outside the image) ; all threads of the CTA participate
+// stage rows y-1, y, y+1 of image n (zeros outside the image) ; all threads of the CTA participate.
+// Asynchronous 16-byte copies (cp.async, zero-fill for rows outside the image): every thread has its 24 copies in flight
+// at once; the first version's load -> store loop exposed one global-memory latency per iteration (~7 us per image row).
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cls_stage_rows(uint8_t* rows, const bf16* __restrict__ u2, int n, int y) {
   for (int i = threadIdx.x; i < 3 * 2 * (CLS_PITCH / 16); i += blockDim.x) {        // left / right border pixels
     const int r = i / (2 * (CLS_PITCH / 16)), rem = i % (2 * (CLS_PITCH / 16));
     const int side = rem / (CLS_PITCH / 16), ch = rem % (CLS_PITCH / 16);
     *reinterpret_cast<uint4*>(rows + r * CLS_ROW_BYTES + (side ? (CLS_W + 1) : 0) * CLS_PITCH + ch * 16) = make_uint4(0, 0, 0, 0);
   }
+  const uint32_t rows_s = smem_u32(rows);
   for (int i = threadIdx.x; i < 3 * CLS_W * 16; i += blockDim.x) {
     const int r = i / (CLS_W * 16), rem = i % (CLS_W * 16);
     const int px = rem >> 4, ch = rem & 15;
     const int yy = y + r - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (yy >= 0 && yy < CLS_H) v = *reinterpret_cast<const uint4*>(u2 + (((size_t)n * CLS_H + yy) * CLS_W + px) * CLS_C + ch * 8);
-    *reinterpret_cast<uint4*>(rows + r * CLS_ROW_BYTES + (px + 1) * CLS_PITCH + ch * 16) = v;
+    const bool ok = yy >= 0 && yy < CLS_H;
+    const bf16* src = ok ? u2 + (((size_t)n * CLS_H + yy) * CLS_W + px) * CLS_C + ch * 8 : u2;
+    cp_async16(rows_s + r * CLS_ROW_BYTES + (px + 1) * CLS_PITCH + ch * 16, src, ok ? 16 : 0);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // logits[n,o,y,x] = bias[o] + sum_{ky,kx,c} u2[n, y+ky-1, x+kx-1, c] * w[o,c,ky,kx]        (NCHW fp32 output)
@@ -325,10 +398,9 @@ extern "C" int ccd_bn_stats(const void* x, int ldx, float* sums_zeroed, int M, i
 
 extern "C" int ccd_bn_apply_relu(const void* x, int ldx, const float* mean, const float* rstd, const float* gamma, const float* beta,
                                  void* y, int ldy, int M, int C, void* stream) {
-  if (!x || !y || !mean || !rstd || !gamma || !beta || M <= 0 || (C & 7)) return CCD_ERR_ARG;
-  const size_t total = (size_t)M * (C / 8);
-  bn_apply_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, mean, rstd, gamma, beta,
-                                                                                          (bf16*)y, ldy, M, C);
+  if (!x || !y || !mean || !rstd || !gamma || !beta || M <= 0 || (C & 7) || C > 256 || (256 % (C / 8))) return CCD_ERR_ARG;
+  bn_apply_relu_kernel<<<(M + BN_APPLY_ROWS - 1) / BN_APPLY_ROWS, bn_block(C), 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, ldx, mean, rstd, gamma, beta, (bf16*)y, ldy, M, C);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }
@@ -350,15 +422,14 @@ extern "C" int ccd_bn_bwd_reduce(const void* dy, int dy_is_f32, int lddy, const 
 extern "C" int ccd_bn_bwd_apply(const void* dy, int dy_is_f32, int lddy, const void* x, int ldx, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, const float* sums, float inv_m, void* dx, int lddx, int M, int C,
                                 void* stream) {
-  if (!dy || !x || !sums || !dx || M <= 0 || (C & 7)) return CCD_ERR_ARG;
-  const size_t total = (size_t)M * (C / 8);
-  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (!dy || !x || !sums || !dx || M <= 0 || (C & 7) || C > 256 || (256 % (C / 8))) return CCD_ERR_ARG;
+  const unsigned blocks = (unsigned)((M + BN_APPLY_ROWS - 1) / BN_APPLY_ROWS);
   if (dy_is_f32)
-    bn_bwd_apply_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, lddy, (const bf16*)x, ldx, mean, rstd, gamma, beta, sums, inv_m,
-                                                                        (bf16*)dx, lddx, M, C);
+    bn_bwd_apply_kernel<true><<<blocks, bn_block(C), 0, (cudaStream_t)stream>>>(dy, lddy, (const bf16*)x, ldx, mean, rstd, gamma, beta, sums,
+                                                                                inv_m, (bf16*)dx, lddx, M, C);
   else
-    bn_bwd_apply_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, lddy, (const bf16*)x, ldx, mean, rstd, gamma, beta, sums, inv_m,
-                                                                         (bf16*)dx, lddx, M, C);
+    bn_bwd_apply_kernel<false><<<blocks, bn_block(C), 0, (cudaStream_t)stream>>>(dy, lddy, (const bf16*)x, ldx, mean, rstd, gamma, beta, sums,
+                                                                                 inv_m, (bf16*)dx, lddx, M, C);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }
