@@ -395,12 +395,13 @@ __device__ __forceinline__ AuxPack<EPI> aux_load(const GemmParams& p, int row, i
   return r;
 }
 
+// returns the fp32 values behind what was stored (EPI_DGELU: the column sums of the output are its consumer)
 template <int EPI>
-__device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, int col, float4 v, const AuxPack<EPI>& x) {
+__device__ __forceinline__ float4 epilogue_row_aux(const GemmParams& p, int row, int col, float4 v, const AuxPack<EPI>& x) {
 #if CCD_DBG_EPI == 1
   if (__float_as_uint(v.x) != 0x7fc12345u) {       // never true for real data: keeps the math, drops the stores
     v.x = v.y + v.z;
-    if (__float_as_uint(v.x) != 0x7fc12346u) return;
+    if (__float_as_uint(v.x) != 0x7fc12346u) return v;
   }
 #endif
   const size_t off = (size_t)row * p.ldc + col;
@@ -415,11 +416,32 @@ __device__ __forceinline__ void epilogue_row_aux(const GemmParams& p, int row, i
     const float2 d0 = __fmul2_rn(make_float2(v.x, v.y), dgelu_fast2(make_float2(bf16lo(x.a), bf16hi(x.a))));
     const float2 d1 = __fmul2_rn(make_float2(v.z, v.w), dgelu_fast2(make_float2(bf16lo(x.b), bf16hi(x.b))));
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + off) = make_uint2(pack_bf16x2(d0.x, d0.y), pack_bf16x2(d1.x, d1.y));
+    return make_float4(d0.x, d0.y, d1.x, d1.y);
   } else if constexpr (EPI == EPI_POS) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + off) =
         make_float4(v.x + __uint_as_float(x.a), v.y + __uint_as_float(x.b), v.z + __uint_as_float(x.c), v.w + __uint_as_float(x.d));
   } else {
     epilogue_row<EPI>(p, row, col, v);
+  }
+  return v;
+}
+
+// EPI_DGELU with out1 != NULL: out1[col] += sum over rows of the fp32 output (= bias gradient of the layer whose
+// pre-activation gradient this GEMM produces; replaces a separate column-sum pass over the [T, 4E] tensor).
+// cs = this thread's sums over its 8 rows of the chunk; lanes sharing (lane & 7) hold the same 4 columns.
+__device__ __forceinline__ void colsum_flush(float* __restrict__ dst, int col, float4 cs, int sub_row, bool col_ok) {
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+    cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+    cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+  }
+  if (sub_row == 0 && col_ok) {
+    atomicAdd(dst + col, cs.x);
+    atomicAdd(dst + col + 1, cs.y);
+    atomicAdd(dst + col + 2, cs.z);
+    atomicAdd(dst + col + 3, cs.w);
   }
 }
 
@@ -630,6 +652,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
           }
           __syncwarp();                          // the 4 KB transpose buffer is rewritten by the next chunk
+          float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             int orow = row_base + i * 4 + sub_row;
@@ -639,7 +662,11 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
               const int a = rem / cs.W, b = rem - a * cs.W;
               orow = (n_img * 2 * cs.H + 2 * a + cs.py) * (2 * cs.W) + 2 * b + cs.px;
             }
-            epilogue_row_aux<EPI>(p, orow, col, v[i], ax[i]);
+            const float4 o4 = epilogue_row_aux<EPI>(p, orow, col, v[i], ax[i]);
+            if constexpr (EPI == EPI_DGELU) { csum.x += o4.x; csum.y += o4.y; csum.z += o4.z; csum.w += o4.w; }
+          }
+          if constexpr (EPI == EPI_DGELU) {
+            if (p.out1 != nullptr) colsum_flush(reinterpret_cast<float*>(p.out1), col, csum, sub_row, true);
           }
           continue;
         }
@@ -662,6 +689,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         for (int j = 0; j < 8; ++j)              // thread = row `lane`; 16-byte chunk j lands at j ^ (row & 7)
           *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) * 4)) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
         __syncwarp();
+        float4 csum_m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + sub_row;
@@ -675,8 +703,12 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
               const int a = rem / cs.W, b = rem - a * cs.W;
               orow = (n_img * 2 * cs.H + 2 * a + cs.py) * (2 * cs.W) + 2 * b + cs.px;
             }
-            epilogue_row_aux<EPI>(p, orow, col, v, ax[i]);
+            const float4 o4 = epilogue_row_aux<EPI>(p, orow, col, v, ax[i]);
+            if constexpr (EPI == EPI_DGELU) { csum_m.x += o4.x; csum_m.y += o4.y; csum_m.z += o4.z; csum_m.w += o4.w; }
           }
+        }
+        if constexpr (EPI == EPI_DGELU) {
+          if (p.out1 != nullptr) colsum_flush(reinterpret_cast<float*>(p.out1), col, csum_m, sub_row, col_ok);
         }
         __syncwarp();                            // the 4 KB transpose buffer is rewritten by the next chunk
       }
@@ -760,6 +792,7 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
   if (ldc <= 0) ldc = N;
   if ((epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_POS) && !aux) return CCD_ERR_ARG;
   if (epi == EPI_GELU && !out1) return CCD_ERR_ARG;
+  if (epi == EPI_DGELU && out1 && g_gemm_variant != 1) return CCD_ERR_UNSUPPORTED;   // fused column sums: persistent kernel only
   const int kb_total = (K + GEMM_BK - 1) / GEMM_BK;
   if (splits < 1) splits = 1;
   if (splits > kb_total) splits = kb_total;

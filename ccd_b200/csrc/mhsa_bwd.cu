@@ -26,8 +26,10 @@ struct MhsaBwdParams {
   const bf16* o;      // [T, E] forward output
   const bf16* d_o;    // [T, E]
   const float* lse2;  // [S, H, 256]
-  const float* delta; // [S, H, 256]  rowsum(O * dO), produced by mhsa_delta_kernel
+  const float* delta; // [S, H, 256]  rowsum(O * dO), produced by mhsa_delta_kernel (pipelined kernel: -delta * scale)
+  const float* nlse;  // [S, H, 256]  -lse2 (pipelined kernel only)
   bf16* dqkv;         // [T, 3E]
+  float* dbias;       // optional [3E] (caller zero-fills): column sums of dqkv = gradient of Attention.qkv.bias
   int E, H;
   float scale, scale_log2;
 };
@@ -78,8 +80,11 @@ __device__ __forceinline__ void store_tmem_row64(uint32_t taddr, bf16* dst) {
 
 // delta[s,h,q] = sum_d O[q, h*64+d] * dO[q, h*64+d]: one warp per token row, 16-byte loads, 8 lanes per head.
 // (Inside the main kernel this prologue was ~30 % of the stall samples: 32 rows x 16 B per load instruction.)
+// nlse != NULL (pipelined main kernel): writes -delta * scale and nlse = -lse2, the forms its inner loop consumes, so that the
+// TMA producer can drop both vectors into shared memory with two bulk copies per item.
 __global__ void __launch_bounds__(256) mhsa_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o,
-                                                         float* __restrict__ delta, int T, int E, int H) {
+                                                         float* __restrict__ delta, const float* __restrict__ lse2,
+                                                         float* __restrict__ nlse, float scale, int T, int E, int H) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= T) return;
@@ -93,7 +98,58 @@ __global__ void __launch_bounds__(256) mhsa_delta_kernel(const bf16* __restrict_
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if ((lane & 7) == 0 && c < nchunk) delta[((size_t)s * H + (c >> 3)) * ATB_N + q] = acc;
+    if ((lane & 7) == 0 && c < nchunk) {
+      const size_t idx = ((size_t)s * H + (c >> 3)) * ATB_N + q;
+      if (nlse != nullptr) {
+        delta[idx] = -acc * scale;
+        nlse[idx] = -lse2[idx];
+      } else {
+        delta[idx] = acc;
+      }
+    }
+  }
+}
+
+// qkv-bias gradient = column sums of dqkv, produced by the pipelined kernel itself:
+//   query part  sum_q dQ[q, d]   and value part  sum_keys dV[key, d]   from the TMEM tiles as they are written out (below);
+//   key part    sum_keys dK[key, d] = sum_q (sum_keys dS[q, key]) Q[q, d] = 0 identically, because sum_keys dS[q, :] =
+//   scale (P . dP - delta[q]) = 0 (a key bias shifts every score of a row by the same amount): left untouched.
+// Per-CTA partial sums live in shared memory across all items of the persistent CTA and are flushed with one global atomic
+// per (head, column) at the end (per-item global atomics concentrate on ~12 L2 slices and throttle: measured 0.65 ms).
+// 64 fp32 TMEM columns of this thread's lane -> bf16 -> 128 contiguous bytes in global memory, and (colsum != NULL) the sums
+// of the 64 columns over the 32 rows of this warp -> atomicAdd(colsum[0..63]) (shared memory).  Value-halving butterfly:
+// 31 shuffles per 32 columns, lane l ends up with the total of column l.
+__device__ __forceinline__ void store_tmem_row64_colsum(uint32_t taddr, bf16* dst, float* colsum, int lane) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t raw[32];
+    tmem_ld_32x32(taddr + half * 32, raw);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(raw[8 * g + 0]), __uint_as_float(raw[8 * g + 1]));
+      o.y = pack_bf16x2(__uint_as_float(raw[8 * g + 2]), __uint_as_float(raw[8 * g + 3]));
+      o.z = pack_bf16x2(__uint_as_float(raw[8 * g + 4]), __uint_as_float(raw[8 * g + 5]));
+      o.w = pack_bf16x2(__uint_as_float(raw[8 * g + 6]), __uint_as_float(raw[8 * g + 7]));
+      *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = o;
+    }
+    if (colsum != nullptr) {
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const bool up = (lane & step) != 0;
+#pragma unroll
+        for (int k = 0; k < step; ++k) {
+          const float keep = up ? v[k + step] : v[k];
+          const float send = up ? v[k] : v[k + step];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+      }
+      atomicAdd(colsum + half * 32 + lane, v[0]);
+    }
   }
 }
 
@@ -294,10 +350,17 @@ struct MhsaBwd2Smem {
   static constexpr int OFF_DS = 4 * TILE;             // 4 sub-blocks [128 keys x 64 queries] bf16, 16 KB each
   static constexpr int OFF_LSE = 6 * TILE;            // 2 x 256 f32 (double buffered per item): -lse2
   static constexpr int OFF_DELTA = OFF_LSE + 2048;    // 2 x 256 f32: delta * scale
-  static constexpr int OFF_BAR = OFF_DELTA + 2048;
+  static constexpr int OFF_CSUM = OFF_DELTA + 2048;   // [2 (q, v)][8 heads][64] f32 column sums of dQ / dV of this CTA's items
+  static constexpr int OFF_BAR = OFF_CSUM + 4096;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
+// 1-D bulk copy global -> shared (TMA engine), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void sts128_b(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -342,6 +405,8 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
   }
+  float* csum = reinterpret_cast<float*>(smem + L::OFF_CSUM);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) csum[i] = 0.f;
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -360,7 +425,10 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         const int s = w / p.H, h = w - s * p.H;
         const int row0 = s * ATB_N;
         mbar_wait(bar_done, (it & 1) ^ 1);            // previous item's MMAs no longer read Q/K/V/dO (passes for it = 0)
-        mbar_arrive_expect_tx(bar_qk, 2 * L::TILE);
+        mbar_arrive_expect_tx(bar_qk, 2 * L::TILE + 2048);
+        // -lse2 and -delta*scale of the item's 256 queries (pre-formed by mhsa_delta_kernel), double buffered per item
+        bulk_load_1d(smem + L::OFF_LSE + (it & 1) * 1024, p.nlse + (size_t)w * ATB_N, 1024, bar_qk);
+        bulk_load_1d(smem + L::OFF_DELTA + (it & 1) * 1024, p.delta + (size_t)w * ATB_N, 1024, bar_qk);
         for (int b = 0; b < 2; ++b) {
           tma_load_2d(smem + L::OFF_K + b * 16384, &tmQKV, bar_qk, p.E + h * ATB_D, row0 + b * 128);
           tma_load_2d(smem + L::OFF_Q + b * 16384, &tmQKV, bar_qk, h * ATB_D, row0 + b * 128);
@@ -442,7 +510,6 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const int tid = g * 128 + r;                      // 0..255 <-> query row for the lse / delta staging
     const uint32_t sLse = smem_u32(smem + L::OFF_LSE), sDel = smem_u32(smem + L::OFF_DELTA);
     const uint32_t sDS = smem_u32(smem + L::OFF_DS);
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
@@ -451,12 +518,7 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       const int s_idx = w / p.H, h = w - s_idx * p.H;
       const int row0 = s_idx * ATB_N;
       const int par = it & 1;
-      {
-        const size_t gi = ((size_t)s_idx * p.H + h) * ATB_N + tid;
-        reinterpret_cast<float*>(smem + L::OFF_LSE)[par * 256 + tid] = -p.lse2[gi];
-        reinterpret_cast<float*>(smem + L::OFF_DELTA)[par * 256 + tid] = -p.delta[gi] * p.scale;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(bar_qk, it & 1);                      // the item's -lse2 / -delta*scale vectors have landed (bulk copies)
 #pragma unroll 1
       for (int s = g; s < 8; s += 2) {
         const int j = s >> 2, qs = s & 3;
@@ -516,11 +578,12 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           mbar_wait(bar_acc, j);
           tc_fence_after();
           bf16* drow = p.dqkv + ((size_t)row0 + j * 128 + r) * (3 * p.E) + h * ATB_D;
+          const bool want_bias = p.dbias != nullptr;
           if (g == 0) store_tmem_row64(tDK + lane_sel, drow + p.E);
-          else        store_tmem_row64(tDV + lane_sel, drow + 2 * p.E);
+          else        store_tmem_row64_colsum(tDV + lane_sel, drow + 2 * p.E, want_bias ? csum + 512 + h * 64 : nullptr, lane);
           if (j == 1) {
             bf16* qrow = p.dqkv + ((size_t)row0 + g * 128 + r) * (3 * p.E) + h * ATB_D;
-            store_tmem_row64(tDQ + g * 64 + lane_sel, qrow);
+            store_tmem_row64_colsum(tDQ + g * 64 + lane_sel, qrow, want_bias ? csum + h * 64 : nullptr, lane);
           }
           tc_fence_before();
           mbar_arrive(bar_epi);
@@ -531,20 +594,28 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbias != nullptr) {          // flush this CTA's column sums: q part at [0, E), v part at [2E, 3E)
+    for (int i = threadIdx.x; i < 2 * p.H * 64; i += blockDim.x) {
+      const int part = i / (p.H * 64), c = i - part * (p.H * 64);
+      const float v = csum[part * 512 + c];
+      if (v != 0.f) atomicAdd(p.dbias + part * 2 * p.E + c, v);
+    }
+  }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
-
-static int g_mhsa_bwd_variant = 1;   // 1 = pipelined persistent kernel (default), 0 = one CTA per (sequence, head)
 
 }  // namespace ccd
 
 using namespace ccd;
 
 // C ABI -- see include/ccd_b200.h
+static int g_mhsa_bwd_variant = 1;   // 1 = pipelined persistent kernel (default), 0 = one CTA per (sequence, head)
+
 extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, float* delta_ws, void* dqkv,
-                            int S, int H, void* stream_) {
+                            float* dbias_qkv, int S, int H, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!qkv || !o || !d_o || !lse2 || !delta_ws || !dqkv || S <= 0 || H <= 0) return CCD_ERR_ARG;
+  if (!qkv || !o || !d_o || !lse2 || !delta_ws || !dqkv || S <= 0 || H <= 0 || H > 8) return CCD_ERR_ARG;
+  if (dbias_qkv != nullptr && g_mhsa_bwd_variant != 1) return CCD_ERR_UNSUPPORTED;   // fused bias gradient: pipelined kernel only
   const int E = H * ATB_D;
   CUtensorMap tmQKV, tmDO;
   if (!get_tmap_bf16_2d(&tmQKV, qkv, (uint64_t)S * ATB_N, (uint64_t)3 * E, (uint64_t)3 * E, 128, 64)) return CCD_ERR_TMAP;
@@ -555,6 +626,7 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
   p.lse2 = lse2;
   p.delta = delta_ws;
   p.dqkv = reinterpret_cast<bf16*>(dqkv);
+  p.dbias = dbias_qkv;
   p.E = E;
   p.H = H;
   p.scale = 0.125f;
@@ -565,7 +637,10 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
                                         MhsaBwdSmem::SMEM_BYTES));
     attr_set = true;
   }
-  mhsa_delta_kernel<<<(S * ATB_N + 7) / 8, 256, 0, stream>>>(p.o, p.d_o, delta_ws, S * ATB_N, E, H);
+  const bool pipelined = g_mhsa_bwd_variant == 1;
+  float* nlse_ws = pipelined ? delta_ws + (size_t)S * H * ATB_N : nullptr;      // second half of the workspace
+  p.nlse = nlse_ws;
+  mhsa_delta_kernel<<<(S * ATB_N + 7) / 8, 256, 0, stream>>>(p.o, p.d_o, delta_ws, lse2, nlse_ws, p.scale, S * ATB_N, E, H);
   CCD_LAUNCH_CHECK();
   if (g_mhsa_bwd_variant == 1) {
     static bool attr2_set = false;

@@ -284,9 +284,8 @@ class VitFn(torch.autograd.Function):
             # ---- MLP branch: x3 = x2 + s*(gelu(xn2 W1^T + b1) W2^T + b2);  dxb = s * dx (bf16) ----
             ops.linear_wgrad(dxb, hact, grads[pi + 10])             # fc2.bias grad came from the producer of dxb
             dh = torch.empty(T, 4 * E, **b16)
-            ops.linear_dgrad(dxb, wfc2, ops.EPI_DGELU, dh, hpre)
+            ops.linear_dgrad(dxb, wfc2, ops.EPI_DGELU, dh, hpre, colsum=grads[pi + 9])    # fc1.bias grad in the epilogue
             ops.linear_wgrad(dh, xn2, grads[pi + 8])
-            ops.colsum_bf16(dh, grads[pi + 9])
             dxn2 = torch.empty(T, E, **b16)
             ops.linear_dgrad(dh, wfc1, ops.EPI_BF16, dxn2)
             dx2, dx2b = ops.layernorm_bwd(x2, g2, dxn2, dx, grads[pi + 6], grads[pi + 7], bf16_seq_scale=ds_attn,
@@ -295,9 +294,8 @@ class VitFn(torch.autograd.Function):
             ops.linear_wgrad(dx2b, o, grads[pi + 4])                # proj.bias grad came from the LN2 backward above
             d_o = torch.empty(T, E, **b16)
             ops.linear_dgrad(dx2b, wproj, ops.EPI_BF16, d_o)
-            dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, n, H)
+            dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, n, H, dbias=grads[pi + 3])              # qkv.bias grad in the same kernels
             ops.linear_wgrad(dqkv, xn, grads[pi + 2])
-            ops.colsum_bf16(dqkv, grads[pi + 3])
             dxn = torch.empty(T, E, **b16)
             ops.linear_dgrad(dqkv, wqkv, ops.EPI_BF16, dxn)
             prev_scale = None

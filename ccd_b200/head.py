@@ -133,20 +133,17 @@ class HeadFn(torch.autograd.Function):
         gb3 = torch.zeros(bott, dtype=torch.float32, device=dev)
         ops.linear_wgrad(dh3, a2, gw3)
         ops.colsum_bf16(dh3, gb3)
-        dp2 = torch.empty(R2, hid, **b16)
-        ops.linear_dgrad(dh3, wb[2], ops.EPI_DGELU, dp2, p2)
-        # mlp[2]
+        # mlp[2] / mlp[0]: their bias gradients (column sums of dp2 / dp1) come out of the GELU' epilogues
         gw2 = torch.zeros(hid, hid, dtype=torch.float32, device=dev)
         gb2 = torch.zeros(hid, dtype=torch.float32, device=dev)
-        ops.linear_wgrad(dp2, a1, gw2)
-        ops.colsum_bf16(dp2, gb2)
-        dp1 = torch.empty(R2, hid, **b16)
-        ops.linear_dgrad(dp2, wb[1], ops.EPI_DGELU, dp1, p1)
-        # mlp[0]
         gw1 = torch.zeros(hid, E, dtype=torch.float32, device=dev)
         gb1 = torch.zeros(hid, dtype=torch.float32, device=dev)
+        dp2 = torch.empty(R2, hid, **b16)
+        ops.linear_dgrad(dh3, wb[2], ops.EPI_DGELU, dp2, p2, colsum=gb2)
+        ops.linear_wgrad(dp2, a1, gw2)
+        dp1 = torch.empty(R2, hid, **b16)
+        ops.linear_dgrad(dp2, wb[1], ops.EPI_DGELU, dp1, p1, colsum=gb1)
         ops.linear_wgrad(dp1, xb, gw1)
-        ops.colsum_bf16(dp1, gb1)
         dx = torch.empty(R2, E, dtype=torch.float32, device=dev)
         ops.linear_dgrad(dp1, wb[0], ops.EPI_F32, dx)
         return (dx, None, None, gw1, gb1, gw2, gb2, gw3, gb3, dg if ctx.needs_input_grad[9] else None, dv)

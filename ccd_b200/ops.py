@@ -48,6 +48,7 @@ def _bind():
         _FN["ccd_set_option"](0, int(os.environ["CCD_GEMM_VARIANT"]))
     if "CCD_MHSA_BWD_VARIANT" in os.environ:        # 1 = pipelined persistent [default], 0 = first version
         _FN["ccd_set_mhsa_bwd_variant"](int(os.environ["CCD_MHSA_BWD_VARIANT"]))
+        _MHSA_BWD_VARIANT[0] = 1 if int(os.environ["CCD_MHSA_BWD_VARIANT"]) else 0
 
 
 def _call(name, *args, work=None):
@@ -113,11 +114,12 @@ def linear_fwd(x_bf16, w_bf16, bias, epi, out0, out1=None, aux=None, seq_scale=N
     return gemm(x_bf16, w_bf16, T, N, K, 0, 0, epi, bias, out0, out1, aux, seq_scale=seq_scale)
 
 
-def linear_dgrad(dy_bf16, w_bf16, epi, out0, aux=None):
-    """dx [T,K] = dy [T,N] @ w [N,K]: w is read MN-major (no transpose copy)."""
+def linear_dgrad(dy_bf16, w_bf16, epi, out0, aux=None, colsum=None):
+    """dx [T,K] = dy [T,N] @ w [N,K]: w is read MN-major (no transpose copy).  EPI_DGELU: `colsum` (optional, zero-filled
+    f32 [K]) accumulates the column sums of the fp32 result in the epilogue (bias gradient of the layer below)."""
     T, N = dy_bf16.shape
     K = w_bf16.shape[1]
-    return gemm(dy_bf16, w_bf16, T, K, N, 0, 1, epi, None, out0, None, aux)
+    return gemm(dy_bf16, w_bf16, T, K, N, 0, 1, epi, None, out0, colsum, aux)
 
 
 def linear_wgrad(dy_bf16, x_bf16, dw_f32_zeroed):
@@ -143,11 +145,19 @@ def mhsa_fwd(qkv, S, H, want_lse=True, variant=None):
     return out, lse
 
 
-def mhsa_bwd(qkv, o, d_o, lse, S, H):
+_MHSA_BWD_VARIANT = [1]
+
+
+def mhsa_bwd(qkv, o, d_o, lse, S, H, dbias=None):
+    """dqkv of the fused attention; `dbias` (optional, zero-filled f32 [3E]) accumulates the qkv-bias gradient in the
+    same kernels (pipelined variant) or through a column-sum pass over dqkv (first variant)."""
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty_like(lse)
-    _call("ccd_mhsa_bwd", _p(qkv), _p(o), _p(_chk(d_o, torch.bfloat16)), _p(lse), _p(delta), _p(dqkv), S, H, _s(),
-          work=(10.0 * 256 * 256 * 64 * S * H, (S, H)))
+    delta = torch.empty((2,) + tuple(lse.shape), dtype=torch.float32, device=lse.device)     # workspace [2,S,H,256]
+    fused = dbias is not None and _MHSA_BWD_VARIANT[0] == 1
+    _call("ccd_mhsa_bwd", _p(qkv), _p(o), _p(_chk(d_o, torch.bfloat16)), _p(lse), _p(delta), _p(dqkv), _p(dbias) if fused else None,
+          S, H, _s(), work=(10.0 * 256 * 256 * 64 * S * H, (S, H)))
+    if dbias is not None and not fused:
+        colsum_bf16(dqkv, dbias)
     return dqkv
 
 
@@ -155,6 +165,7 @@ def set_mhsa_bwd_variant(v):
     """1 = pipelined persistent backward kernel (default), 0 = first version (A/B switch, see include/ccd_b200.h)."""
     _bind()
     _FN["ccd_set_mhsa_bwd_variant"](int(v))
+    _MHSA_BWD_VARIANT[0] = 1 if int(v) else 0
 
 
 def layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=False):

@@ -28,7 +28,7 @@ extern "C" {
 #define CCD_EPI_GELU 1  /* out0 bf16 = acc + bias (may be NULL: inference) ; out1 bf16 = gelu_erf(acc + bias)  (Mlp.fc1+act, vision_transformer.py:59-61) */
 #define CCD_EPI_RESID 2 /* out0 f32 = aux_f32 + s[m/256]*(acc + bias); s = DropPath keep-scale (vision_transformer.py:27-36) or NULL;                         (x = x + f(x), vision_transformer.py:109-110) */
 #define CCD_EPI_F32 3   /* out0 f32 = acc + bias ; split-K slices accumulate atomically (caller zero-fills)  */
-#define CCD_EPI_DGELU 4 /* out0 bf16 = acc * gelu'(aux_bf16)                        (autograd of nn.GELU)   */
+#define CCD_EPI_DGELU 4 /* out0 bf16 = acc * gelu'(aux_bf16)                        (autograd of nn.GELU); out1 (optional, f32 [N], caller zero-fills) += column sums of the fp32 output = bias gradient of the layer below */
 #define CCD_EPI_POS 5   /* out0 f32 = acc + bias + aux_f32[(m % 256), :]            (prepare_tokens, vision_transformer.py:225-236) */
 
 /* tcgen05/TMEM/TMA GEMM: C[M,N] = A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulate.
@@ -44,10 +44,14 @@ int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, int a_mn, i
  * variant 1: P staged through shared memory.  Replaces Attention.forward core, vision_transformer.py:85-89. */
 int ccd_mhsa_fwd(const void* qkv, void* out, float* lse2, int S, int H, int variant, void* stream);
 
-/* Fused MHSA backward: -> dqkv bf16 [S*256, 3*H*64]; delta_ws = f32 [S,H,256] workspace (rowsum(O*dO), written by a
- * small pre-pass).  Replaces autograd of vision_transformer.py:85-89. */
-int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, float* delta_ws, void* dqkv, int S, int H,
-                 void* stream);
+/* Fused MHSA backward: -> dqkv bf16 [S*256, 3*H*64]; delta_ws = f32 [2,S,H,256] workspace (rowsum(O*dO) and the negated
+ * log-sum-exp in the form the main kernel consumes, written by a small pre-pass).  Replaces autograd of vision_transformer.py:85-89. */
+int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, float* delta_ws, void* dqkv,
+                 float* dbias_qkv, int S, int H, void* stream);
+/* dbias_qkv (optional, f32 [3*H*64], caller zero-fills): gradient of Attention.qkv.bias = column sums of dqkv, accumulated by
+ * the backward kernel itself from the dQ and dV tiles as they leave TMEM (per-CTA partial sums in shared memory, one
+ * global atomic per (head, column) and CTA); the key part is identically zero (a key bias shifts all scores of a row
+ * equally) and is left untouched.  Pipelined variant only (CCD_ERR_UNSUPPORTED otherwise). */
 /* A/B switch (debug): 1 = pipelined persistent backward kernel (default), 0 = first version (one CTA per (sequence, head)) */
 int ccd_set_mhsa_bwd_variant(int value);
 

@@ -97,10 +97,12 @@ def test_gemm_epilogues(ops, N):
     # dGELU
     hpre = _bf(torch.randn(M, N, device="cuda", generator=g))
     out_b = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    ops.gemm(A, B, M, N, K, 0, 0, ops.EPI_DGELU, None, out_b, None, hpre)
+    csum = torch.zeros(N, device="cuda")
+    ops.gemm(A, B, M, N, K, 0, 0, ops.EPI_DGELU, None, out_b, csum, hpre)          # out1 = fused column sums
     x = hpre.float().requires_grad_(True)
     O.gelu(x).sum().backward()
     assert _rel(out_b.float(), (acc - bias) * x.grad) < 5e-3
+    assert _rel(csum, ((acc - bias) * x.grad).sum(0)) < 2e-3
     # positional epilogue
     pos = torch.randn(256, N, device="cuda", generator=g)
     ops.gemm(A, B, M, N, K, 0, 0, ops.EPI_POS, bias, out, None, pos)
@@ -140,9 +142,10 @@ def test_mhsa_bwd(ops, S, H, variant):
     qkv = _bf(torch.randn(S * 256, 3 * H * 64, device="cuda", generator=g))
     d_o = _bf(torch.randn(S * 256, H * 64, device="cuda", generator=g))
     o, lse = ops.mhsa_fwd(qkv, S, H, True, 0)
+    dbias = torch.zeros(3 * H * 64, device="cuda")
     ops.set_mhsa_bwd_variant(variant)
     try:
-        dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, S, H)
+        dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, S, H, dbias=dbias)
         torch.cuda.synchronize()
     finally:
         ops.set_mhsa_bwd_variant(1)
@@ -154,6 +157,11 @@ def test_mhsa_bwd(ops, S, H, variant):
     for name, sl in (("dq", slice(0, E)), ("dk", slice(E, 2 * E)), ("dv", slice(2 * E, 3 * E))):
         r = _rel(dqkv[:, sl].float(), x.grad[:, sl])
         assert r < 2e-2, (name, r)
+    # qkv-bias gradient = column sums of dqkv (fused: q from the dQ tiles, v = column sums of d_o, k identically zero)
+    want = x.grad.sum(0)
+    scale = want.abs().max().item()
+    assert (dbias.double() - want).abs().max().item() < 2e-2 * scale, ((dbias.double() - want).abs().max().item(), scale)
+    assert want[E:2 * E].abs().max().item() < 1e-6 * scale          # the key part vanishes analytically
 
 
 # ---------------------------------------------------------------------------------------------------------
