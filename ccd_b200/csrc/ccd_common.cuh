@@ -57,6 +57,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the hardware parks the thread until the phase completes or the hint expires,
+// instead of returning after its short default slice.  ncu on the persistent GEMM: the default form made the three
+// single-lane role warps (two TMA producers, the MMA issuer) execute 21 % of all instructions of the kernel in their
+// wait loops, on the same schedulers as the epilogue warps.  CCD_MBAR_SUSPEND_NS=0 restores the default form.
+#ifndef CCD_MBAR_SUSPEND_NS
+#define CCD_MBAR_SUSPEND_NS 20000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity) {
+#if CCD_MBAR_SUSPEND_NS == 0
+  return mbar_try_wait(bar, parity);
+#else
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)CCD_MBAR_SUSPEND_NS)
+      : "memory");
+  return ok != 0;
+#endif
+}
 // Bounded wait: a protocol bug traps (CUDA error at the next sync) instead of hanging the GPU box.
 #ifndef CCD_MBAR_TIMEOUT_CYCLES
 #define CCD_MBAR_TIMEOUT_CYCLES (4000000000LL)  // ~2 s at 1.9 GHz
@@ -64,7 +86,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_suspend(bar, parity)) {
     if (clock64() - t0 > CCD_MBAR_TIMEOUT_CYCLES) {
       printf("[ccd_b200] mbarrier timeout block (%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x, parity);

@@ -47,6 +47,7 @@ struct GemmParams {
   int atomic;            // EPI_F32: accumulate with atomicAdd
   const float* seq_scale;  // EPI_RESID only: per-sequence (row / 256) scale of the branch (DropPath,
                            // vision_transformer.py:27-36); null = 1
+  int direct;              // full tiles take the transpose-free epilogue (32-byte aligned rows, no split-K atomics)
 };
 
 // Implicit-GEMM ("spatial") operand description for the SegHead convolutions (Dino/modules/segmentor.py:37-95): the
@@ -379,6 +380,39 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
+// 256-bit global accesses (LDG.256 / STG.256): one full 32-byte sector per lane
+__device__ __forceinline__ void stg256(void* gptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* gptr, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(gptr));
+}
+__device__ __forceinline__ void ldg256_nc(const void* gptr, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(gptr));
+}
+
+// Sum over the 32 lanes of each of a thread's 32 values (thread = row, value j = column j): a transposing butterfly,
+// the number of live values halves at every exchange; afterwards lane l holds the total of column l.  31 SHFL.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 template <int EPI>
 __device__ __forceinline__ AuxPack<EPI> aux_load(const GemmParams& p, int row, int col) {
   AuxPack<EPI> r{0u, 0u, 0u, 0u};
@@ -608,6 +642,127 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
         }
       }
+      if (p.direct && (row_base + 32 <= p.M) && (n0 + BN <= p.N)) {
+        // ---- transpose-free epilogue for full tiles: thread = row, straight from the tcgen05.ld registers ----
+        // Every lane owns 32 consecutive columns of its own output row per chunk: 64 B (bf16) / 128 B (fp32), moved with
+        // 256-bit global accesses (one full 32-byte sector per lane: tools/ubench/st_rows.cu measures 5.3 TB/s for this
+        // pattern against 5.8 TB/s for row-contiguous warps).  The staging-buffer transpose it replaces cost 16 shared-memory
+        // wavefront-instructions per chunk and warp, i.e. ~2000 cycles of the SM's shared-memory pipe per 128x256 tile --
+        // the same pipe tcgen05.mma reads its operands through (2300 cycles per tile at K = 384): with the transpose the
+        // tile period was 7400 cycles against 4100 for the main loop alone (tools/ubench/mma_rate.cu).
+        const int row = row_base + lane;
+        int orow = row;
+        if (SPATIAL && cs.out_rowmap) {          // ConvTranspose2d stride 2: scatter to the (py, px) parity positions
+          const int hw = cs.H * cs.W;
+          const int n_img = orow / hw, rem = orow - n_img * hw;
+          const int a = rem / cs.W, b = rem - a * cs.W;
+          orow = (n_img * 2 * cs.H + 2 * a + cs.py) * (2 * cs.W) + 2 * b + cs.px;
+        }
+        const int nb = n0 + g * (BN / 2);        // first column of this group's half of the tile
+        const size_t ooff = (size_t)orow * p.ldc + nb;
+        const size_t aoff = (EPI == EPI_POS) ? (size_t)(row & 255) * p.ldc + nb : (size_t)row * p.ldc + nb;
+        // the group's BN/2 bias values -> this warp's staging buffer (read back as warp-wide broadcasts)
+        const uint32_t bias_s = smem_u32(stage);
+        if (4 * lane < BN / 2) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 4 * lane));
+          sts128(bias_s + (uint32_t)lane * 16u, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+        }
+        float sc = 1.0f;
+        if constexpr (EPI == EPI_RESID) {
+          if (p.seq_scale != nullptr) sc = __ldg(p.seq_scale + (row >> 8));
+        }
+        __syncwarp();
+        mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < CHUNKS_PER_GROUP; ++cc) {
+          constexpr int AUXW = (EPI == EPI_RESID || EPI == EPI_POS) ? 32 : (EPI == EPI_DGELU) ? 16 : 1;
+          uint32_t ax[AUXW];
+          if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ldg256(reinterpret_cast<const float*>(p.aux) + aoff + cc * 32 + k * 8, ax + 8 * k);
+          } else if constexpr (EPI == EPI_POS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ldg256_nc(reinterpret_cast<const float*>(p.aux) + aoff + cc * 32 + k * 8, ax + 8 * k);
+          } else if constexpr (EPI == EPI_DGELU) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) ldg256(reinterpret_cast<const bf16*>(p.aux) + aoff + cc * 32 + k * 16, ax + 8 * k);
+          }
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + (g * CHUNKS_PER_GROUP + cc) * 32), raw);
+          tmem_wait_ld();
+          if (cc == CHUNKS_PER_GROUP - 1) {      // this group's half of the accumulator is read: hand it back to the MMA issuer
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+#if CCD_DBG_EPI == 3
+          if (raw[0] != 0x7fc12345u) continue;
+#endif
+          float2 f[16];                          // acc + bias, column pairs
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = lds128(bias_s + (uint32_t)(cc * 128 + j * 16));
+            f[2 * j] = __fadd2_rn(make_float2(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1])), make_float2(b.x, b.y));
+            f[2 * j + 1] = __fadd2_rn(make_float2(__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])), make_float2(b.z, b.w));
+          }
+          if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU) {
+            uint32_t o[16];
+            if (EPI == EPI_BF16 || p.out0 != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(f[j].x, f[j].y);
+              bf16* dst = reinterpret_cast<bf16*>(p.out0) + ooff + cc * 32;
+              stg256(dst, o);
+              stg256(dst + 16, o + 8);
+            }
+            if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 gl = gelu_fast2(f[j]);
+                o[j] = pack_bf16x2(gl.x, gl.y);
+              }
+              bf16* dst = reinterpret_cast<bf16*>(p.out1) + ooff + cc * 32;
+              stg256(dst, o);
+              stg256(dst + 16, o + 8);
+            }
+          } else if constexpr (EPI == EPI_DGELU) {
+            uint32_t o[16];
+            float d[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 r = __fmul2_rn(f[j], dgelu_fast2(make_float2(bf16lo(ax[j]), bf16hi(ax[j]))));
+              o[j] = pack_bf16x2(r.x, r.y);
+              d[2 * j] = r.x;
+              d[2 * j + 1] = r.y;
+            }
+            bf16* dst = reinterpret_cast<bf16*>(p.out0) + ooff + cc * 32;
+            stg256(dst, o);
+            stg256(dst + 16, o + 8);
+            if (p.out1 != nullptr) {             // bias gradient of the layer below: column sums of the fp32 result
+              const float tot = warp_colsum32(d, lane);
+              atomicAdd(reinterpret_cast<float*>(p.out1) + nb + cc * 32 + lane, tot);
+            }
+          } else {                               // fp32 outputs: EPI_RESID / EPI_POS / EPI_F32 (no split-K)
+            uint32_t o[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float2 r = f[j];
+              if constexpr (EPI == EPI_RESID) {
+                r = __ffma2_rn(r, make_float2(sc, sc), make_float2(__uint_as_float(ax[2 * j]), __uint_as_float(ax[2 * j + 1])));
+              } else if constexpr (EPI == EPI_POS) {
+                r = __fadd2_rn(r, make_float2(__uint_as_float(ax[2 * j]), __uint_as_float(ax[2 * j + 1])));
+              }
+              o[2 * j] = __float_as_uint(r.x);
+              o[2 * j + 1] = __float_as_uint(r.y);
+            }
+            float* dst = reinterpret_cast<float*>(p.out0) + ooff + cc * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) stg256(dst + 8 * k, o + 8 * k);
+          }
+        }
+        __syncwarp();                            // the bias staging is rewritten for the next tile
+        continue;
+      }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       // Full tiles (every row and column valid) take a branch-free path: all eight staging loads of a chunk are issued
@@ -721,6 +876,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 }
 
 static int g_gemm_variant = 1;   // 1 = persistent (default), 0 = one tile per CTA
+static int g_gemm_epilogue = 1;  // full-tile epilogue: 1 = per-shape choice (default), 0 = shared-memory transpose everywhere, 2 = transpose-free everywhere
 
 template <int EPI, int BN, bool SPATIAL>
 static int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits,
@@ -804,6 +960,21 @@ extern "C" int ccd_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
   p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0; p.kb_per_split = kb_per;
   p.bias = bias; p.out0 = out0; p.out1 = out1; p.aux = aux; p.ldc = ldc; p.atomic = (splits > 1) ? 1 : 0;
   p.seq_scale = seq_scale;
+  {
+    // transpose-free epilogue: 256-bit accesses need 32-byte aligned row segments of every output / auxiliary tensor
+    const size_t es0 = (epi == EPI_RESID || epi == EPI_F32 || epi == EPI_POS) ? 4 : 2;
+    const size_t esa = (epi == EPI_DGELU) ? 2 : 4;
+    // Measured per shape (tools/kbench.py, ViT-Small batch 256): the thread-per-row epilogue wins where one bf16 output
+    // (or a long-K fp32 residual tile) leaves the LSU tag stage idle -- 170 vs 178 us for fc1+GELU without the saved
+    // pre-activation, 1-2 % on the plain bf16 GEMMs and the K = 1536 residual GEMM -- and loses where two tensors per tile
+    // go through sector-per-lane accesses (GELU with saved pre-activation, GELU', K = 384 residual GEMM: 10-28 % slower).
+    bool ok = !p.atomic && (g_gemm_epilogue == 2 ||
+                            (g_gemm_epilogue == 1 && (epi == EPI_BF16 || (epi == EPI_GELU && out0 == nullptr) || (epi == EPI_RESID && K >= 1024))));
+    ok = ok && (((size_t)ldc * es0) % 32 == 0) && (out0 == nullptr || ((uintptr_t)out0 % 32) == 0);
+    if (epi == EPI_GELU) ok = ok && ((uintptr_t)out1 % 32) == 0;
+    if (epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_POS) ok = ok && (((size_t)ldc * esa) % 32 == 0) && ((uintptr_t)aux % 32) == 0;
+    p.direct = ok ? 1 : 0;
+  }
   if (g_gemm_variant == 1) {
     switch (epi) {
       case EPI_BF16:  return dispatch_gemm_persistent<EPI_BF16>(A, B, p, splits, stream);
@@ -878,6 +1049,8 @@ extern "C" int ccd_conv_gemm(const void* sp, const void* other, int M, int N, in
   p.M = M; p.N = N; p.K = K; p.kb_per_split = kb_per;
   p.bias = bias; p.out0 = out0; p.out1 = nullptr; p.aux = nullptr; p.ldc = ldc; p.atomic = (splits > 1) ? 1 : 0;
   p.seq_scale = nullptr;
+  p.direct = (!p.atomic && (g_gemm_epilogue == 2 || (g_gemm_epilogue == 1 && epi == EPI_BF16)) &&
+              (((size_t)ldc * (epi == EPI_F32 ? 4 : 2)) % 32 == 0) && ((uintptr_t)out0 % 32) == 0) ? 1 : 0;
 
   int bn;
   CUtensorMap tmA, tmB;
@@ -911,8 +1084,10 @@ extern "C" int ccd_conv_gemm(const void* sp, const void* other, int M, int N, in
 #undef CCD_CONV_LAUNCH
 }
 
-// debug / A-B switch: key 0 = GEMM variant (1 persistent, 0 one-tile-per-CTA)
+// debug / A-B switch: key 0 = GEMM variant (1 persistent, 0 one-tile-per-CTA); key 1 = epilogue of full tiles
+// (1 per-shape choice [default], 0 shared-memory transpose, 2 transpose-free thread-per-row wherever alignment allows)
 extern "C" int ccd_set_option(int key, int value) {
   if (key == 0) { g_gemm_variant = value ? 1 : 0; return CCD_OK; }
+  if (key == 1) { g_gemm_epilogue = (value < 0 || value > 2) ? 1 : value; return CCD_OK; }
   return CCD_ERR_ARG;
 }

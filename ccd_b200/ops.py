@@ -46,6 +46,8 @@ def _bind():
     import os
     if "CCD_GEMM_VARIANT" in os.environ:            # debug A/B switch (1 = persistent [default], 0 = one tile per CTA)
         _FN["ccd_set_option"](0, int(os.environ["CCD_GEMM_VARIANT"]))
+    if "CCD_GEMM_EPILOGUE" in os.environ:           # debug A/B switch (1 = per-shape [default], 0 = smem transpose, 2 = thread-per-row)
+        _FN["ccd_set_option"](1, int(os.environ["CCD_GEMM_EPILOGUE"]))
     if "CCD_MHSA_BWD_VARIANT" in os.environ:        # 1 = pipelined persistent [default], 0 = first version
         _FN["ccd_set_mhsa_bwd_variant"](int(os.environ["CCD_MHSA_BWD_VARIANT"]))
         _MHSA_BWD_VARIANT[0] = 1 if int(os.environ["CCD_MHSA_BWD_VARIANT"]) else 0
@@ -159,6 +161,13 @@ def mhsa_bwd(qkv, o, d_o, lse, S, H, dbias=None):
     if dbias is not None and not fused:
         colsum_bf16(dqkv, dbias)
     return dqkv
+
+
+def set_gemm_epilogue(v):
+    """Full-tile epilogue of the persistent GEMM: 1 = per-shape choice (default), 0 = shared-memory transpose, 2 = transpose-free
+    thread-per-row wherever alignment allows (A/B switch, see include/ccd_b200.h:ccd_set_option)."""
+    _bind()
+    _FN["ccd_set_option"](1, int(v))
 
 
 def set_mhsa_bwd_variant(v):

@@ -156,7 +156,9 @@ int ccd_seg_cls_fwd(const void* u2, const float* w, const float* bias, float* lo
 int ccd_seg_cls_dgrad(const float* dl, const float* w, void* du2_bf16, int n_img, void* stream);
 int ccd_seg_cls_wgrad(const void* u2, const float* dl, float* dw_zeroed, float* dbias_zeroed, int n_img, void* stream);
 
-/* debug / A-B switches (process-global): key 0 = GEMM variant (1 = persistent [default], 0 = one tile per CTA) */
+/* debug / A-B switches (process-global): key 0 = GEMM variant (1 = persistent [default], 0 = one tile per CTA);
+   key 1 = epilogue of full tiles in the persistent GEMM (1 = per-shape choice [default], 0 = shared-memory transpose,
+   2 = transpose-free thread-per-row wherever alignment allows) */
 int ccd_set_option(int key, int value);
 
 /* library identification (build sanity) */

@@ -30,8 +30,16 @@ def _rel(a, b):
 # ---------------------------------------------------------------------------------------------------------
 # GEMM: every majorness combination and epilogue
 # ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(params=[0, 2, 1], ids=["smem-transpose", "thread-per-row", "auto"])
+def gemm_epilogue(ops, request):
+    """Both full-tile epilogue implementations of the persistent GEMM (and the per-shape default)."""
+    ops.set_gemm_epilogue(request.param)
+    yield request.param
+    ops.set_gemm_epilogue(1)
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 384, 384), (512, 1152, 192), (52, 256, 2048), (300, 192, 448), (128, 128, 64)])
-def test_gemm_kmajor_bf16_bias(ops, M, N, K):
+def test_gemm_kmajor_bf16_bias(ops, M, N, K, gemm_epilogue):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
     A = _bf(torch.randn(M, K, device="cuda", generator=g))
     B = _bf(torch.randn(N, K, device="cuda", generator=g) * 0.1)
@@ -45,7 +53,7 @@ def test_gemm_kmajor_bf16_bias(ops, M, N, K):
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(384, 1536, 1024), (192, 64, 520), (256, 256, 52)])
-def test_gemm_majorness_f32(ops, a_mn, b_mn, M, N, K):
+def test_gemm_majorness_f32(ops, a_mn, b_mn, M, N, K, gemm_epilogue):
     g = torch.Generator(device="cuda").manual_seed(11 + a_mn * 2 + b_mn)
     A = _bf(torch.randn(M, K, device="cuda", generator=g))
     B = _bf(torch.randn(N, K, device="cuda", generator=g))
@@ -71,7 +79,7 @@ def test_gemm_splitk_atomic(ops):
 
 
 @pytest.mark.parametrize("N", [768, 1152, 200])      # N-tile 256 / 192 / 128 (ragged, column masking)
-def test_gemm_epilogues(ops, N):
+def test_gemm_epilogues(ops, N, gemm_epilogue):
     import ccd_oracle as O
     M, K = 512, 384
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -94,6 +102,9 @@ def test_gemm_epilogues(ops, N):
     out = torch.empty(M, N, device="cuda")
     ops.gemm(A, B, M, N, K, 0, 0, ops.EPI_RESID, bias, out, None, res)
     assert _rel(out, acc + res) < 1e-5
+    scale = torch.rand(M // 256, device="cuda", generator=g)          # DropPath scale per 256-row sequence
+    ops.gemm(A, B, M, N, K, 0, 0, ops.EPI_RESID, bias, out, None, res, seq_scale=scale)
+    assert _rel(out, acc * scale.repeat_interleave(256)[:, None] + res) < 1e-5
     # dGELU
     hpre = _bf(torch.randn(M, N, device="cuda", generator=g))
     out_b = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
