@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.environ.get("CCD_LIB", os.path.join(HERE, "libccd_b200.so"))   # CCD_LIB: experiment builds (tools/)
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ccd_b200.h")
-SOURCES = ["gemm_umma.cu", "mhsa_fwd.cu", "mhsa_bwd.cu", "rowwise.cu", "dino_loss.cu", "charseg.cu", "seghead.cu", "optim.cu", "abi.cu"]
+SOURCES = ["gemm_umma.cu", "mhsa_fwd.cu", "mhsa_bwd.cu", "rowwise.cu", "dino_loss.cu", "charseg.cu", "seghead.cu", "optim.cu", "decoder.cu", "abi.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-cudart", "static"]

@@ -14,7 +14,8 @@ MT_CAST_BF16, MT_EMA, MT_SCALE, MT_SQNORM, MT_CLIP = 0, 1, 2, 3, 4
 LN_EPS = 1e-6
 SLOTS = 26
 
-_CTYPE = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong}
+_CTYPE = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
+          "unsigned long long": ctypes.c_ulonglong}
 _FN = {}
 LAUNCHES = [0]     # number of kernels launched through the C ABI (bench.py reports it)
 KERNELS_PER_CALL = {"ccd_dino_ce_fwd": 2, "ccd_seg_ce_fwd": 2, "ccd_char_plan": 3, "ccd_mhsa_bwd": 2}
@@ -177,21 +178,22 @@ def set_mhsa_bwd_variant(v):
     _MHSA_BWD_VARIANT[0] = 1 if int(v) else 0
 
 
-def layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=False):
+def layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=False, eps=LN_EPS):
     rows, E = x.shape
     yb = torch.empty(rows, E, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     yf = torch.empty(rows, E, dtype=torch.float32, device=x.device) if want_f32 else None
-    _call("ccd_layernorm_fwd", _p(_chk(x, torch.float32)), _p(gamma), _p(beta), _p(yb), _p(yf), rows, E, LN_EPS, _s())
+    _call("ccd_layernorm_fwd", _p(_chk(x, torch.float32)), _p(gamma), _p(beta), _p(yb), _p(yf), rows, E, eps, _s())
     return yb, yf
 
 
-def layernorm_bwd(x, gamma, dy, resid, dgamma, dbeta, want_f32=True, want_bf16=True, bf16_seq_scale=None, dbias_next=None):
+def layernorm_bwd(x, gamma, dy, resid, dgamma, dbeta, want_f32=True, want_bf16=True, bf16_seq_scale=None, dbias_next=None,
+                  eps=LN_EPS):
     rows, E = x.shape
     assert dy.is_contiguous() and dy.shape == x.shape
     dxf = torch.empty(rows, E, dtype=torch.float32, device=x.device) if want_f32 else None
     dxb = torch.empty(rows, E, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     _call("ccd_layernorm_bwd", _p(x), _p(gamma), _p(dy), 1 if dy.dtype == torch.bfloat16 else 0, _p(resid), _p(dxf), _p(dxb),
-          _p(dgamma), _p(dbeta), _p(bf16_seq_scale), _p(dbias_next), rows, E, LN_EPS, _s())
+          _p(dgamma), _p(dbeta), _p(bf16_seq_scale), _p(dbias_next), rows, E, eps, _s())
     return dxf, dxb
 
 
@@ -512,3 +514,41 @@ def seg_cls_wgrad(u2, dl, n_img):
     buf = torch.zeros(2 * 128 * 9 + 2, dtype=torch.float32, device=dl.device)
     _call("ccd_seg_cls_wgrad", _p(u2), _p(_chk(dl, torch.float32)), _p(buf), _p(buf[2304:]), n_img, _s())
     return buf[:2304].view(2, 128, 3, 3), buf[2304:]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# recognition / fine-tuning decoder (include/ccd_b200.h: ccd_dec_attn_*, ccd_tf_ce, ccd_dropout)
+# ------------------------------------------------------------------------------------------------------------
+def dec_attn_fwd(q, k, v, n, heads, tq, tk, trg=None, pad_idx=0, p_drop=0.0, seed=0, want_lse=True):
+    """q [n*tq, ldq], k / v [n*tk, ld] bf16 column views (head h = columns [64h, 64h+64)); returns o [n*tq, 64*heads], lse."""
+    o = torch.empty(n * tq, heads * 64, dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(n, heads, tq, dtype=torch.float32, device=q.device) if want_lse else None
+    _call("ccd_dec_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(trg),
+          pad_idx, n, heads, tq, tk, float(p_drop), int(seed), _s())
+    return o, lse
+
+
+def dec_attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, n, heads, tq, tk, trg=None, pad_idx=0, p_drop=0.0, seed=0):
+    """Writes dq / dk / dv (bf16 column views with the layouts of q / k / v)."""
+    assert d_o.stride(0) == o.stride(0)
+    _call("ccd_dec_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), _p(d_o), o.stride(0), _p(lse),
+          _p(trg), pad_idx, _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), n, heads, tq, tk, float(p_drop),
+          int(seed), _s())
+
+
+def tf_ce(logits, n_classes, targets, pad_idx):
+    """logits f32 [n*t, ld]; returns (acc [2] = loss sum, counted rows; dlogits f32 [n*t, ld] = softmax - onehot)."""
+    n, t = targets.shape
+    acc = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits)
+    _call("ccd_tf_ce", _p(_chk(logits, torch.float32)), logits.shape[1], n_classes, _p(targets), n, t, pad_idx, _p(acc), _p(dl), _s())
+    return acc, dl
+
+
+def dropout(x, p, seed, resid=None, out_dtype=None):
+    """out = resid + keep(seed, i) * x / (1 - p)  (nn.Dropout with a regenerable mask; the backward is the same call on dy)."""
+    out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    assert x.is_contiguous() and (resid is None or (resid.is_contiguous() and resid.dtype == torch.float32))
+    _call("ccd_dropout", _p(x), 1 if x.dtype == torch.bfloat16 else 0, _p(resid), _p(out), 1 if out.dtype == torch.bfloat16 else 0,
+          x.numel(), float(p), int(seed), _s())
+    return out

@@ -65,6 +65,14 @@ def fill_state_dict(shapes, seed=0, std=0.02):
             out[name] = 1.0 + 0.1 * torch.rand(shape, generator=g)
         elif leaf == "running_mean":
             out[name] = 0.01 * torch.randn(shape, generator=g)
+        elif leaf == "position_table":                      # PositionalEncoding buffer (transformer_module.py:138-149): a constant
+            import numpy as np
+            d = shape[-1]
+            den = torch.Tensor([1.0 / np.power(10000, 2 * (j // 2) / d) for j in range(d)]).view(1, -1)
+            tab = torch.arange(shape[-2]).unsqueeze(-1).float() * den
+            tab[:, 0::2] = torch.sin(tab[:, 0::2])
+            tab[:, 1::2] = torch.cos(tab[:, 1::2])
+            out[name] = tab.reshape(shape)
         elif leaf == "weight_g":
             out[name] = 1.0 + 0.05 * torch.randn(shape, generator=g)
         elif leaf == "weight" and len(shape) == 1:          # LayerNorm / BatchNorm scale
@@ -74,3 +82,24 @@ def fill_state_dict(shapes, seed=0, std=0.02):
         else:
             out[name] = std * torch.randn(shape, generator=g)
     return out
+
+
+def finetune_config(arch="vit_small", drop_path_rate=0.0):
+    """The attribute bag DINO_Finetune reads (Dino/configs/CCD_vision_model_ARD.yaml:62-85 flattened as train_finetune.py does)."""
+    import types
+    return types.SimpleNamespace(arch=arch, patch_size=4, drop_path_rate=drop_path_rate, decoder_max_seq_len=25, decoder_n_layers=6,
+                                 decoder_d_embedding=512, decoder_n_head=8, decoder_d_k=64, decoder_d_v=64, decoder_d_model=512,
+                                 decoder_d_inner=256)
+
+
+def make_targets(n, seed=0, max_seq_len=25, start_idx=91, pad_idx=92):
+    """Synthetic label tensors framed like AttnConvertor.str2tensor (Dino/convertor/attn.py:87-105): BOS, 1..max_seq_len-2
+    characters in 0..89, EOS (= BOS index), PAD up to max_seq_len  (SURVEY.md section 8d, cfg5)."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.full((n, max_seq_len), pad_idx, dtype=torch.long)
+    for i in range(n):
+        ln = int(torch.randint(1, max_seq_len - 1, (1,), generator=g))
+        t[i, 0] = start_idx
+        t[i, 1:1 + ln] = torch.randint(0, 90, (ln,), generator=g)
+        t[i, 1 + ln] = start_idx
+    return t

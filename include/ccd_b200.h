@@ -156,6 +156,33 @@ int ccd_seg_cls_fwd(const void* u2, const float* w, const float* bias, float* lo
 int ccd_seg_cls_dgrad(const float* dl, const float* w, void* du2_bf16, int n_img, void* stream);
 int ccd_seg_cls_wgrad(const void* u2, const float* dl, float* dw_zeroed, float* dbias_zeroed, int n_img, void* stream);
 
+/* ---- recognition / fine-tuning decoder (BASELINE config 5) ----
+ * Attention of the NRTR decoder (Dino/decoder/transformer_module.py:9-96): o = dropout(softmax(mask(q k^T / 8))) v per
+ * (sample, head), d_k = d_v = 64, tq <= 32 queries, tk <= 256 keys.  q/k/v/o are bf16 matrices [n*tq or n*tk, ld] whose
+ * columns [64h, 64h+64) belong to head h (so fused QKV / KV projection outputs are read in place).
+ * trg != NULL (self-attention, tk == tq): key j is visible to query i iff j <= i and trg[n, j] != pad_idx
+ * (get_pad_mask & get_subsequent_mask, Dino/decoder/nrtr_decoder.py:82-96); trg == NULL: no mask (src_mask is None).
+ * p_drop = ScaledDotProductAttention.dropout on the probabilities (0 = evaluation); the mask is a pure function of
+ * (seed, sample, head, i, j): the backward regenerates it.  lse [n, heads, tq] (natural log) is kept for the backward. */
+int ccd_dec_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, float* lse,
+                     const long long* trg, int pad_idx, int n, int heads, int tq, int tk, float p_drop, unsigned long long seed,
+                     void* stream);
+int ccd_dec_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, const void* d_o, int ldo,
+                     const float* lse, const long long* trg, int pad_idx, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
+                     int n, int heads, int tq, int tk, float p_drop, unsigned long long seed, void* stream);
+
+/* TFLoss (Dino/loss/ce_loss.py:94-128): cross-entropy of logits[:, :-1] against targets[:, 1:], pad_idx ignored.
+ * logits f32 [n*t, ld] (first n_classes columns valid); acc_zeroed[0] += sum of row losses, acc_zeroed[1] += counted rows
+ * (loss = acc[0] / acc[1]); dlogits f32 [n*t, ld] = softmax - onehot on counted rows, 0 elsewhere (scale by g / acc[1]). */
+int ccd_tf_ce(const float* logits, int ld, int n_classes, const long long* targets, int n, int t, int pad_idx, float* acc_zeroed,
+              float* dlogits, void* stream);
+
+/* nn.Dropout (+ residual): out[i] = resid[i] + keep(seed, i) * x[i] / (1 - p); resid may be NULL; x / out f32 or bf16.
+ * The same call with the same seed applied to the output gradient is the backward (Dino/decoder/transformer_module.py:70,
+ * :116; Dino/model/dino_vision.py:124). */
+int ccd_dropout(const void* x, int x_is_bf16, const float* resid, void* out, int out_is_bf16, long long n, float p,
+                unsigned long long seed, void* stream);
+
 /* debug / A-B switches (process-global): key 0 = GEMM variant (1 = persistent [default], 0 = one tile per CTA);
    key 1 = epilogue of full tiles in the persistent GEMM (1 = per-shape choice [default], 0 = shared-memory transpose,
    2 = transpose-free thread-per-row wherever alignment allows) */
