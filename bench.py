@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repository's sm_100a path
     python bench.py --impl reference ...                      # the reference algorithm's CPU path (oracle port) on host cores
+    python bench.py --workload finetune [--impl reference]    # BASELINE config 5: recognition fine-tuning step, batch 512
 
 One "step" = one full pretraining step of train.py:221-275 on one synthetic batch:
 student fwd + teacher fwd + DINO/seg loss + backward (+DDP all-reduce) + per-parameter clip + AdamW + teacher EMA +
@@ -23,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "CCD pretrain images/sec (ViT-Small, 3x32x128)"
+METRIC_FT = "CCD finetune images/sec (ViT-Small, 3x32x128)"       # BASELINE.json config 5 (python bench.py --workload finetune)
 ARCH_DIMS = {"vit_tiny": 192, "vit_small": 384, "vit_base": 512}
 
 
@@ -32,6 +34,17 @@ def f_sample(E, rbar=8.5):
     f_head = 2 * (E * 2048 + 2048 * 2048 + 2048 * 256 + 256 * 65536)
     f_seg = 3 * (2 * 256 * E * 9 * 128 + 2 * 256 * 128 * 64) + 2 * 256 * 192 * 128 * 16 + 2 * 1024 * 128 * 128 * 16 + 2 * 4096 * 128 * 9 * 2
     return 8 * f_vit + 8 * rbar * f_head + 6 * f_seg
+
+
+def f_sample_finetune(E, t=25):
+    """Algorithmic FLOPs per image of one fine-tuning step (fwd + bwd = 3x fwd): ViT over ONE view, Mlp E->512->512 over the
+    256 tokens, the K/V projections of the 6 cross-attentions over the 256 tokens, 6 decoder layers over T = 25 target
+    positions (self q/k/v + fc, cross q + fc, FFN 512->256->512, both attentions), classifier 512->92."""
+    f_vit = 2 * 256 * 48 * E + 12 * (6 * 256 * E * E + 4 * (E // 64) * 256 * 256 * 64 + 2 * 256 * E * E + 16 * 256 * E * E)
+    f_mlp = 2 * 256 * (E * 512 + 512 * 512)
+    f_kv = 6 * 2 * 256 * 512 * 1024
+    f_layer = t * 2 * (512 * 1536 + 512 * 512 + 2 * 512 * 512 + 2 * 512 * 256) + 4 * 8 * 64 * t * (t + 256)
+    return 3 * (f_vit + f_mlp + f_kv + 6 * f_layer + 2 * t * 512 * 92)
 
 
 def measured_peaks():
@@ -125,9 +138,52 @@ def usable_cores():
     return max(1, min(n, int(os.environ.get("CCD_CPU_THREADS", "64"))))
 
 
+def cpu_reference_arm_finetune(args, as_line):
+    """Fine-tuning workload: the oracle restatement of DINO_Finetune.forward_train (oracle/finetune_oracle.py, pinned against
+    the unmodified reference) on the host cores: fwd + TFLoss + bwd of one synthetic batch, fp32, all threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import finetune_oracle as FO
+    from ccd_b200 import synthetic as S
+    from ccd_b200.finetune import DINO_Finetune
+    cores = usable_cores()
+    torch.set_num_threads(cores)
+    B = max(args.cpu_batch, 8)
+    shapes = {k: v.shape for k, v in DINO_Finetune(S.finetune_config("vit_small")).state_dict().items()}
+    sd = {k: v.requires_grad_(v.dtype.is_floating_point and "position_table" not in k) for k, v in S.fill_state_dict(shapes, 0).items()}
+    img = torch.randn(B, 3, 32, 128, generator=torch.Generator().manual_seed(1234))
+    tgt = S.make_targets(B, seed=1234)
+    steps, warm = (args.steps, args.warmup) if as_line else (2, 1)
+    budget = float(os.environ.get("CCD_CPU_BUDGET_S", "150" if as_line else "40"))
+    times, t_begin = [], time.perf_counter()
+    for i in range(warm + steps):
+        if times and time.perf_counter() - t_begin > budget:
+            break
+        t0 = time.perf_counter()
+        L, _, _ = FO.finetune_forward_train(sd, "vit_small", img, tgt)
+        L.backward()
+        for v in sd.values():
+            v.grad = None
+        if i >= warm or (i == warm - 1 and time.perf_counter() - t_begin > budget):
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    cb = {"value": B / sec, "unit": "images/s", "cores": cores, "kind": "port",
+          "sample": f"oracle (fp32 torch restatement of the reference DINO_Finetune) ViT-Small fwd+TFLoss+bwd, batch {B}, "
+                    f"{len(times)} timed step(s) of {sec:.2f} s"}
+    if not as_line:
+        return cb
+    print(json.dumps({"metric": METRIC_FT, "value": B / sec, "unit": "images/s", "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
+                      "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "impl": "reference",
+                      "config": {"workload": "ViT-Small CCD finetune step (encoder + NRTR decoder + TFLoss), bounded CPU sample", "batch": B},
+                      "cpu_baseline": cb, "e2e": {"value": B / sec, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def cpu_reference_arm(args, as_line):
     """The reference algorithm's own CPU path (oracle/ccd_oracle.py, pinned against the unmodified reference) on the host
     cores of this box: fwd + loss + bwd of one synthetic batch, fp32, all threads."""
+    if getattr(args, "workload", "pretrain") == "finetune":
+        return cpu_reference_arm_finetune(args, as_line)
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ccd_oracle as O
@@ -227,13 +283,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ccd_b200", choices=["ccd_b200", "reference", "stock-eager-cuda"])
     ap.add_argument("--arch", default="vit_small")
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"],
+                    help="pretrain = BASELINE config 2/3 (the headline metric); finetune = BASELINE config 5 (batch 512)")
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--out-dim", type=int, default=65536)
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write per-shape GEMM/attention timings (json)")
     args = ap.parse_args()
+    finetune = args.workload == "finetune"
+    if args.batch is None:
+        args.batch = 512 if finetune else 256
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,7 +313,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: ccd_b200 has no CPU path (use --impl reference for the CPU baseline)")
     from ccd_b200 import ops, synthetic as S
-    from ccd_b200.trainer import PretrainStep
+    from ccd_b200.trainer import FinetuneStep, PretrainStep
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ddp = world > 1
@@ -262,11 +323,16 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
     B = args.batch
-    trainer = PretrainStep(arch=args.arch, out_dim=args.out_dim, batch_per_gpu=B, drop_path_rate=0.1, device=dev, ddp=ddp)
-    trainer.student.train()
-    x_h, m_h, t_h = S.make_batch(B, seed=1234 + rank)
-    x_h, m_h, t_h = x_h.pin_memory(), m_h.pin_memory(), t_h.pin_memory()
-    x_d, m_d, t_d = x_h.to(dev), m_h.to(dev), t_h.to(dev)
+    if finetune:
+        trainer = FinetuneStep(arch=args.arch, batch_per_gpu=B, drop_path_rate=0.1, device=dev, ddp=ddp)
+        trainer.model.train()
+        host = (torch.randn(B, 3, 32, 128, generator=torch.Generator().manual_seed(1234 + rank)).pin_memory(),
+                S.make_targets(B, seed=1234 + rank).pin_memory())
+    else:
+        trainer = PretrainStep(arch=args.arch, out_dim=args.out_dim, batch_per_gpu=B, drop_path_rate=0.1, device=dev, ddp=ddp)
+        trainer.student.train()
+        host = tuple(t.pin_memory() for t in S.make_batch(B, seed=1234 + rank))
+    resident = tuple(t.to(dev) for t in host)
     # L2 flush between timed iterations is implicit: one step streams > 20 GB of activations through a 126 MB L2
     def barrier():
         if ddp:
@@ -274,7 +340,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(W):
-        trainer.step(x_d, m_d, t_d, sync_loss=False)
+        trainer.step(*resident, sync_loss=False)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ----
@@ -291,7 +357,7 @@ def main():
     for k in range(K):
         if k == K - 1:
             ops.PROFILE = prof
-        loss = trainer.step(x_d, m_d, t_d, sync_loss=False)
+        loss = trainer.step(*resident, sync_loss=False)
     e1.record()
     barrier()
     ops.PROFILE = None
@@ -310,13 +376,13 @@ def main():
         barrier()
         e0.record()
         for _ in range(K):
-            trainer.step(x_h, m_h, t_h, sync_loss=True)          # H2D copies + loss.item() inside
+            trainer.step(*host, sync_loss=True)                  # H2D copies + loss.item() inside
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if ddp:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        h2d = (x_h.numel() + m_h.numel() + t_h.numel()) * 4
+        h2d = sum(t.numel() * t.element_size() for t in host)
         e2e = {"value": B * world * K / (t.item() / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": 4 * world}
 
@@ -357,15 +423,19 @@ def main():
                                       for s, x in v["shapes"].items()}} for k, v in agg.items()}, f, indent=1)
     E = ARCH_DIMS[args.arch]
     value = B * world * K / (ms / 1e3)
+    fs = f_sample_finetune(E) if finetune else f_sample(E)
+    workload = (f"{args.arch} CCD finetune step (train_finetune.py:262-290), batch {B}/GPU, labels T=25 (DICT90), dropout 0.1, "
+                "drop_path 0.1, encoder + Mlp + 6-layer NRTR decoder + TFLoss, fwd+bwd+AdamW") if finetune else (
+        f"{args.arch} CCD pretrain step, batch {B}/GPU, 2 views (reference semantics), out_dim {args.out_dim}, "
+        "drop_path 0.1, fwd+bwd+clip+AdamW+EMA+centre")
     line = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC_FT if finetune else METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"{args.arch} CCD pretrain step, batch {B}/GPU, 2 views (reference semantics), out_dim {args.out_dim}, "
-                               "drop_path 0.1, fwd+bwd+clip+AdamW+EMA+centre", "arch": args.arch, "global_batch": B * world,
+        "config": {"workload": workload, "arch": args.arch, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": "inputs+activations >> L2 (20+ GB streamed per step)",
                    "seg_head": "implicit-GEMM tcgen05 convolutions + BN kernels (ccd_conv_gemm)"},
-        "step_tensor_util": f_sample(E) * value / world / (peak_tf * 1e12),
+        "step_tensor_util": fs * value / world / (peak_tf * 1e12),
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "loss": final_loss,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -32,7 +32,7 @@ __host__ __device__ inline uint32_t drop_threshold(float p) {
   return t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
 }
 
-constexpr int DA_THREADS = 128;
+constexpr int DA_THREADS = 256;
 constexpr int DA_WARPS = DA_THREADS / 32;
 constexpr int DA_D = 64;                    // d_k = d_v
 constexpr int DA_LD = 66;                   // padded row length (bf16 elements) = 33 words
@@ -66,25 +66,38 @@ __device__ __forceinline__ void stage_rows(bf16* dst, const bf16* src, int rows,
     d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
   }
 }
-__device__ __forceinline__ float dot64(const bf16* a, const float* b_f32) {   // a: padded shared row, b: 64 floats in shared
-  float acc = 0.f;
-  const uint32_t* a2 = reinterpret_cast<const uint32_t*>(a);
+// row . x : `row` = padded bf16 row in shared memory (lanes read different rows: 33-word stride, conflict-free),
+// x = 64 floats held in registers by every lane
+__device__ __forceinline__ float dot64(const bf16* row, const float (&x)[DA_D]) {
+  float a0 = 0.f, a1 = 0.f;
+  const uint32_t* r2 = reinterpret_cast<const uint32_t*>(row);
 #pragma unroll
   for (int d = 0; d < 32; ++d) {
-    const uint32_t u = a2[d];
-    acc = fmaf(bf16lo(u), b_f32[2 * d], acc);
-    acc = fmaf(bf16hi(u), b_f32[2 * d + 1], acc);
+    const uint32_t u = r2[d];
+    a0 = fmaf(bf16lo(u), x[2 * d], a0);
+    a1 = fmaf(bf16hi(u), x[2 * d + 1], a1);
   }
-  return acc;
+  return a0 + a1;
+}
+// every lane gets the whole 64-element row (scaled) of a [.., ld] bf16 matrix into registers (warp-wide broadcast loads)
+__device__ __forceinline__ void load_row64(const bf16* row, float scale, float (&x)[DA_D]) {
+  const uint4* r4 = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = __ldg(r4 + c);
+    x[8 * c + 0] = bf16lo(u.x) * scale; x[8 * c + 1] = bf16hi(u.x) * scale;
+    x[8 * c + 2] = bf16lo(u.y) * scale; x[8 * c + 3] = bf16hi(u.y) * scale;
+    x[8 * c + 4] = bf16lo(u.z) * scale; x[8 * c + 5] = bf16hi(u.z) * scale;
+    x[8 * c + 6] = bf16lo(u.w) * scale; x[8 * c + 7] = bf16hi(u.w) * scale;
+  }
 }
 
-// dynamic shared memory: K [tk][66] bf16 | V [tk][66] bf16 | per-warp q row [64] f32 | per-warp probabilities [tk] f32
-__global__ void __launch_bounds__(DA_THREADS) dec_attn_fwd_kernel(const DecAttnParams p) {
+// dynamic shared memory: K [tk][66] bf16 | V [tk][66] bf16 | per-warp probabilities [tk] f32
+__global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_fwd_kernel(const DecAttnParams p) {
   extern __shared__ __align__(16) uint8_t da_smem[];
   bf16* sK = reinterpret_cast<bf16*>(da_smem);
   bf16* sV = sK + p.tk * DA_LD;
-  float* sQ = reinterpret_cast<float*>(sV + p.tk * DA_LD);
-  float* sP = sQ + DA_WARPS * DA_D;
+  float* sP = reinterpret_cast<float*>(sV + p.tk * DA_LD);
   const int n = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_rows(sK, p.k + (size_t)n * p.tk * p.ldk + h * DA_D, p.tk, p.ldk, threadIdx.x);
@@ -92,25 +105,25 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attn_fwd_kernel(const DecAttnP
   __syncthreads();
   const uint32_t thresh = drop_threshold(p.p_drop);
   const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
-  float* myq = sQ + warp * DA_D;
+  const int njj = (p.tk + 31) >> 5;
   float* myp = sP + warp * p.tk;
   for (int i = warp; i < p.tq; i += DA_WARPS) {
-    const bf16* qrow = p.q + ((size_t)n * p.tq + i) * p.ldq + h * DA_D;
-    myq[lane] = __bfloat162float(qrow[lane]) * p.scale;            // (q / temperature) as in the reference
-    myq[lane + 32] = __bfloat162float(qrow[lane + 32]) * p.scale;
-    __syncwarp();
+    float qr[DA_D];
+    load_row64(p.q + ((size_t)n * p.tq + i) * p.ldq + h * DA_D, p.scale, qr);     // (q / temperature) as in the reference
     float s[DA_MAX_TK / 32];
     float mx = -INFINITY;
 #pragma unroll
     for (int jj = 0; jj < DA_MAX_TK / 32; ++jj) {
-      const int j = jj * 32 + lane;
       s[jj] = -INFINITY;
-      if (j < p.tk) {
-        bool vis = true;
-        if (p.trg != nullptr) vis = (j <= i) && (p.trg[(size_t)n * p.tq + j] != (long long)p.pad_idx);
-        if (vis) s[jj] = dot64(sK + j * DA_LD, myq);
+      if (jj < njj) {
+        const int j = jj * 32 + lane;
+        if (j < p.tk) {
+          bool vis = true;
+          if (p.trg != nullptr) vis = (j <= i) && (p.trg[(size_t)n * p.tq + j] != (long long)p.pad_idx);
+          if (vis) s[jj] = dot64(sK + j * DA_LD, qr);
+        }
+        mx = fmaxf(mx, s[jj]);
       }
-      mx = fmaxf(mx, s[jj]);
     }
     mx = warp_max(mx);
     float sum = 0.f;
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attn_fwd_kernel(const DecAttnP
 #pragma unroll
     for (int jj = 0; jj < DA_MAX_TK / 32; ++jj) {
       const int j = jj * 32 + lane;
-      if (j < p.tk) {
+      if (jj < njj && j < p.tk) {
         float pr = s[jj] * inv;
         if (p.p_drop > 0.f) {
           const unsigned long long idx = (((unsigned long long)blockIdx.x * p.tq + i) << 8) + j;
@@ -134,29 +147,35 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attn_fwd_kernel(const DecAttnP
       }
     }
     __syncwarp();
-    float o0 = 0.f, o1 = 0.f;                                     // lane owns output dims 2*lane, 2*lane+1
-    for (int j = 0; j < p.tk; ++j) {
-      const float pr = myp[j];
-      const uint32_t u = reinterpret_cast<const uint32_t*>(sV + j * DA_LD)[lane];
-      o0 = fmaf(pr, bf16lo(u), o0);
-      o1 = fmaf(pr, bf16hi(u), o1);
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;                 // lane owns output dims 2*lane, 2*lane+1 (two partial chains)
+    int j = 0;
+    for (; j + 1 < p.tk; j += 2) {
+      const float p0 = myp[j], p1 = myp[j + 1];
+      const uint32_t u0 = reinterpret_cast<const uint32_t*>(sV + j * DA_LD)[lane];
+      const uint32_t u1 = reinterpret_cast<const uint32_t*>(sV + (j + 1) * DA_LD)[lane];
+      o0 = fmaf(p0, bf16lo(u0), o0); o1 = fmaf(p0, bf16hi(u0), o1);
+      o2 = fmaf(p1, bf16lo(u1), o2); o3 = fmaf(p1, bf16hi(u1), o3);
     }
-    reinterpret_cast<uint32_t*>(p.o + ((size_t)n * p.tq + i) * p.ldo + h * DA_D)[lane] = pack_bf16x2(o0, o1);
+    if (j < p.tk) {
+      const float p0 = myp[j];
+      const uint32_t u0 = reinterpret_cast<const uint32_t*>(sV + j * DA_LD)[lane];
+      o0 = fmaf(p0, bf16lo(u0), o0); o1 = fmaf(p0, bf16hi(u0), o1);
+    }
+    reinterpret_cast<uint32_t*>(p.o + ((size_t)n * p.tq + i) * p.ldo + h * DA_D)[lane] = pack_bf16x2(o0 + o2, o1 + o3);
     if (lane == 0 && p.lse != nullptr) p.lse[((size_t)n * p.heads + h) * p.tq + i] = mx + __logf(sum);
     __syncwarp();
   }
 }
 
-// backward: dynamic shared memory: K | V | Q [tq][66] | dO [tq][66] (bf16) | P~ [tq][tk] f32 | dS [tq][tk] f32 | per-warp row [64] f32 x 2
-__global__ void __launch_bounds__(DA_THREADS) dec_attn_bwd_kernel(const DecAttnParams p) {
+// backward: dynamic shared memory: K | V | Q [tq][66] | dO [tq][66] (bf16) | P~ [tq][tk] bf16 | dS [tq][tk] bf16
+__global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_bwd_kernel(const DecAttnParams p) {
   extern __shared__ __align__(16) uint8_t da_smem[];
   bf16* sK = reinterpret_cast<bf16*>(da_smem);
   bf16* sV = sK + p.tk * DA_LD;
   bf16* sQ = sV + p.tk * DA_LD;
   bf16* sDO = sQ + p.tq * DA_LD;
-  float* sP = reinterpret_cast<float*>(sDO + p.tq * DA_LD);
-  float* sDS = sP + p.tq * p.tk;
-  float* sRow = sDS + p.tq * p.tk;                                // [warps][2][64]
+  bf16* sP = sDO + p.tq * DA_LD;
+  bf16* sDS = sP + p.tq * p.tk;
   const int n = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_rows(sK, p.k + (size_t)n * p.tk * p.ldk + h * DA_D, p.tk, p.ldk, threadIdx.x);
@@ -166,68 +185,82 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attn_bwd_kernel(const DecAttnP
   __syncthreads();
   const uint32_t thresh = drop_threshold(p.p_drop);
   const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
-  float* myq = sRow + warp * 2 * DA_D;
-  float* mydo = myq + DA_D;
+  const int njj = (p.tk + 31) >> 5;
   // ---- phase 1: per query row: P, dP, dS; dQ ----
   for (int i = warp; i < p.tq; i += DA_WARPS) {
-    const uint32_t uq = reinterpret_cast<const uint32_t*>(sQ + i * DA_LD)[lane];
     const uint32_t ud = reinterpret_cast<const uint32_t*>(sDO + i * DA_LD)[lane];
-    myq[2 * lane] = bf16lo(uq) * p.scale; myq[2 * lane + 1] = bf16hi(uq) * p.scale;
-    mydo[2 * lane] = bf16lo(ud); mydo[2 * lane + 1] = bf16hi(ud);
-    // delta_i = dO_i . O_i
     const uint32_t uo = reinterpret_cast<const uint32_t*>(p.o + ((size_t)n * p.tq + i) * p.ldo + h * DA_D)[lane];
-    float delta = bf16lo(ud) * bf16lo(uo) + bf16hi(ud) * bf16hi(uo);
+    float delta = bf16lo(ud) * bf16lo(uo) + bf16hi(ud) * bf16hi(uo);        // delta_i = dO_i . O_i
     delta = warp_sum(delta);
     const float lse = p.lse[((size_t)n * p.heads + h) * p.tq + i];
-    __syncwarp();
+    float pr[DA_MAX_TK / 32];
+    {
+      float x[DA_D];
+      load_row64(p.q + ((size_t)n * p.tq + i) * p.ldq + h * DA_D, p.scale, x);
 #pragma unroll
-    for (int jj = 0; jj < DA_MAX_TK / 32; ++jj) {
-      const int j = jj * 32 + lane;
-      if (j < p.tk) {
-        bool vis = true;
-        if (p.trg != nullptr) vis = (j <= i) && (p.trg[(size_t)n * p.tq + j] != (long long)p.pad_idx);
-        float pr = 0.f, pt = 0.f, ds = 0.f;
-        if (vis) {
-          pr = __expf(dot64(sK + j * DA_LD, myq) - lse);
-          float dp = dot64(sV + j * DA_LD, mydo);                  // d(P~)_ij = dO_i . V_j
-          pt = pr;
-          if (p.p_drop > 0.f) {
-            const unsigned long long idx = (((unsigned long long)blockIdx.x * p.tq + i) << 8) + j;
-            const bool kp = keep_elem(p.seed, idx, thresh);
-            pt = kp ? pr * inv_keep : 0.f;
-            dp = kp ? dp * inv_keep : 0.f;
-          }
-          ds = pr * (dp - delta);
+      for (int jj = 0; jj < DA_MAX_TK / 32; ++jj) {
+        pr[jj] = 0.f;
+        const int j = jj * 32 + lane;
+        if (jj < njj && j < p.tk) {
+          bool vis = true;
+          if (p.trg != nullptr) vis = (j <= i) && (p.trg[(size_t)n * p.tq + j] != (long long)p.pad_idx);
+          if (vis) pr[jj] = __expf(dot64(sK + j * DA_LD, x) - lse);
         }
-        sP[i * p.tk + j] = pt;
-        sDS[i * p.tk + j] = ds;
+      }
+    }
+    {
+      float x[DA_D];
+      load_row64(p.d_o + ((size_t)n * p.tq + i) * p.ldo + h * DA_D, 1.0f, x);
+#pragma unroll
+      for (int jj = 0; jj < DA_MAX_TK / 32; ++jj) {
+        const int j = jj * 32 + lane;
+        if (jj < njj && j < p.tk) {
+          float pt = pr[jj], ds = 0.f;
+          if (pt != 0.f) {
+            float dp = dot64(sV + j * DA_LD, x);                             // d(P~)_ij = dO_i . V_j
+            if (p.p_drop > 0.f) {
+              const unsigned long long idx = (((unsigned long long)blockIdx.x * p.tq + i) << 8) + j;
+              const bool kp = keep_elem(p.seed, idx, thresh);
+              dp = kp ? dp * inv_keep : 0.f;
+              pt = kp ? pt * inv_keep : 0.f;
+            }
+            ds = pr[jj] * (dp - delta);
+          }
+          sP[i * p.tk + j] = __float2bfloat16(pt);
+          sDS[i * p.tk + j] = __float2bfloat16(ds);
+        }
       }
     }
     __syncwarp();
-    float g0 = 0.f, g1 = 0.f;                                     // dQ_i = scale * sum_j dS_ij K_j
-    for (int j = 0; j < p.tk; ++j) {
-      const float ds = sDS[i * p.tk + j];
-      const uint32_t u = reinterpret_cast<const uint32_t*>(sK + j * DA_LD)[lane];
-      g0 = fmaf(ds, bf16lo(u), g0);
-      g1 = fmaf(ds, bf16hi(u), g1);
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;                 // dQ_i = scale * sum_j dS_ij K_j (bf16-rounded dS, like the dK path)
+    int j = 0;
+    for (; j + 1 < p.tk; j += 2) {
+      const float d0 = __bfloat162float(sDS[i * p.tk + j]), d1 = __bfloat162float(sDS[i * p.tk + j + 1]);
+      const uint32_t u0 = reinterpret_cast<const uint32_t*>(sK + j * DA_LD)[lane];
+      const uint32_t u1 = reinterpret_cast<const uint32_t*>(sK + (j + 1) * DA_LD)[lane];
+      g0 = fmaf(d0, bf16lo(u0), g0); g1 = fmaf(d0, bf16hi(u0), g1);
+      g2 = fmaf(d1, bf16lo(u1), g2); g3 = fmaf(d1, bf16hi(u1), g3);
     }
-    reinterpret_cast<uint32_t*>(p.dq + ((size_t)n * p.tq + i) * p.lddq + h * DA_D)[lane] = pack_bf16x2(g0 * p.scale, g1 * p.scale);
-    __syncwarp();
+    if (j < p.tk) {
+      const float d0 = __bfloat162float(sDS[i * p.tk + j]);
+      const uint32_t u0 = reinterpret_cast<const uint32_t*>(sK + j * DA_LD)[lane];
+      g0 = fmaf(d0, bf16lo(u0), g0); g1 = fmaf(d0, bf16hi(u0), g1);
+    }
+    reinterpret_cast<uint32_t*>(p.dq + ((size_t)n * p.tq + i) * p.lddq + h * DA_D)[lane] = pack_bf16x2((g0 + g2) * p.scale, (g1 + g3) * p.scale);
   }
   __syncthreads();
-  // ---- phase 2: dV_j = sum_i P~_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i   (thread = (key j, dim pair)) ----
-  for (int item = threadIdx.x; item < p.tk * 32; item += DA_THREADS) {
-    const int j = item >> 5, dpair = item & 31;
+  // ---- phase 2: dV_j = sum_i P~_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i   (warp = key j, lane = dim pair) ----
+  for (int j = warp; j < p.tk; j += DA_WARPS) {
     float v0 = 0.f, v1 = 0.f, k0 = 0.f, k1 = 0.f;
     for (int i = 0; i < p.tq; ++i) {
-      const float pt = sP[i * p.tk + j], ds = sDS[i * p.tk + j];
-      const uint32_t ud = reinterpret_cast<const uint32_t*>(sDO + i * DA_LD)[dpair];
-      const uint32_t uq = reinterpret_cast<const uint32_t*>(sQ + i * DA_LD)[dpair];
+      const float pt = __bfloat162float(sP[i * p.tk + j]), ds = __bfloat162float(sDS[i * p.tk + j]);
+      const uint32_t ud = reinterpret_cast<const uint32_t*>(sDO + i * DA_LD)[lane];
+      const uint32_t uq = reinterpret_cast<const uint32_t*>(sQ + i * DA_LD)[lane];
       v0 = fmaf(pt, bf16lo(ud), v0); v1 = fmaf(pt, bf16hi(ud), v1);
       k0 = fmaf(ds, bf16lo(uq), k0); k1 = fmaf(ds, bf16hi(uq), k1);
     }
-    reinterpret_cast<uint32_t*>(p.dv + ((size_t)n * p.tk + j) * p.lddv + h * DA_D)[dpair] = pack_bf16x2(v0, v1);
-    reinterpret_cast<uint32_t*>(p.dk + ((size_t)n * p.tk + j) * p.lddk + h * DA_D)[dpair] = pack_bf16x2(k0 * p.scale, k1 * p.scale);
+    reinterpret_cast<uint32_t*>(p.dv + ((size_t)n * p.tk + j) * p.lddv + h * DA_D)[lane] = pack_bf16x2(v0, v1);
+    reinterpret_cast<uint32_t*>(p.dk + ((size_t)n * p.tk + j) * p.lddk + h * DA_D)[lane] = pack_bf16x2(k0 * p.scale, k1 * p.scale);
   }
 }
 
@@ -283,8 +316,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const TIN* __restrict__ x,
 
 static size_t dec_attn_smem(int tq, int tk, bool bwd) {
   size_t s = (size_t)2 * tk * DA_LD * 2;
-  if (!bwd) return s + (size_t)DA_WARPS * DA_D * 4 + (size_t)DA_WARPS * tk * 4;
-  return s + (size_t)2 * tq * DA_LD * 2 + (size_t)2 * tq * tk * 4 + (size_t)DA_WARPS * 2 * DA_D * 4;
+  if (!bwd) return s + (size_t)DA_WARPS * tk * 4;
+  return s + (size_t)2 * tq * DA_LD * 2 + (size_t)2 * tq * tk * 2;
 }
 
 }  // namespace ccd

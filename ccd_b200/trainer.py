@@ -109,3 +109,54 @@ class PretrainStep:
             if not math.isfinite(float(self._loss_host[0])):
                 raise FloatingPointError(f"Loss is {float(self._loss_host[0])}, stopping training")
         return loss
+
+
+class FinetuneStep:
+    """One recognition fine-tuning step as the reference's train_finetune.py:262-290 drives it (BASELINE config 5):
+    H2D (optional) -> DINO_Finetune.forward_train (ViT encoder -> Mlp -> NRTR decoder -> TFLoss) -> loss.mean() -> zero_grad
+    -> backward (+DDP all-reduce; the reference uses single-process DataParallel) -> [clip_grad_norm_ if configured: the shipped
+    configs set clip_grad: ~] -> AdamW with the cosine learning-rate schedule."""
+
+    def __init__(self, arch="vit_small", batch_per_gpu=512, drop_path_rate=0.1, lr=0.0005, weight_decay=0.05, total_iters=100000,
+                 device="cuda", ddp=False, seed=0):
+        from Dino.model.dino_vision import DINO_Finetune
+        from . import synthetic as S
+        from .optim import AdamW
+        torch.manual_seed(seed)
+        self.device = torch.device(device)
+        model = DINO_Finetune(S.finetune_config(arch, drop_path_rate)).to(self.device)       # train_finetune.py:185-189
+        self.module = model
+        self.world = dist.get_world_size() if (ddp and dist.is_initialized()) else 1
+        if ddp and dist.is_initialized():
+            # backbone.cls_token and backbone.norm_seg.* never receive gradients on this path
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[self.device.index], find_unused_parameters=True,
+                                                        gradient_as_bucket_view=True, static_graph=True)
+        self.model = model
+        # train_finetune.py:222-228: AdamW over get_params_groups-style groups (biases / norms without weight decay)
+        self.opt = AdamW(get_params_groups(model), lr=lr, weight_decay=weight_decay)
+        self.lr_sched = cosine_iter_scheduler(lr, 1e-6, total_iters, warmup_iters=min(total_iters // 10, 1000))
+        self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        self._loss_event = torch.cuda.Event()
+        self.iteration = 0
+        self.batch_per_gpu = batch_per_gpu
+
+    def step(self, image_tensors, label_tensors, sync_loss=True):
+        it = self.iteration
+        image_tensors = image_tensors.to(self.device, non_blocking=True)                     # :277-278
+        label_tensors = label_tensors.to(self.device, non_blocking=True)
+        for g in self.opt.param_groups:                                                      # :280-281
+            g["lr"] = float(self.lr_sched[it])
+        losses, _ = self.model(image_tensors, label_tensors, return_loss=True)               # :283
+        loss = losses.mean()                                                                 # :284
+        if sync_loss:
+            self._loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            self._loss_event.record()
+        self.opt.zero_grad(set_to_none=True)                                                 # :285
+        loss.backward()                                                                      # :286
+        self.opt.step()                                                                      # :289
+        self.iteration += 1
+        if sync_loss:
+            self._loss_event.synchronize()
+            if not math.isfinite(float(self._loss_host[0])):
+                raise FloatingPointError(f"Loss is {float(self._loss_host[0])}, stopping training")
+        return loss

@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from ccd_b200 import synthetic as S
-from ccd_b200.trainer import PretrainStep
+from ccd_b200.trainer import FinetuneStep, PretrainStep
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
@@ -22,6 +22,7 @@ ap.add_argument("--arch", default="vit_small")
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--tag", default="n1")
 ap.add_argument("--host", action="store_true", help="feed from pinned host memory + loss read (the e2e path)")
+ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"])
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0"))
@@ -32,21 +33,23 @@ dev = torch.device("cuda", local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
-t = PretrainStep(arch=a.arch, batch_per_gpu=a.batch, device=dev, ddp=world > 1)
-t.student.train()
-x, m, th = S.make_batch(a.batch, seed=1234 + rank)
-if a.host:
-    x, m, th = x.pin_memory(), m.pin_memory(), th.pin_memory()
+if a.workload == "finetune":
+    t = FinetuneStep(arch=a.arch, batch_per_gpu=a.batch, device=dev, ddp=world > 1)
+    t.model.train()
+    batch = (torch.randn(a.batch, 3, 32, 128, generator=torch.Generator().manual_seed(1234 + rank)), S.make_targets(a.batch, seed=1234 + rank))
 else:
-    x, m, th = x.to(dev), m.to(dev), th.to(dev)
+    t = PretrainStep(arch=a.arch, batch_per_gpu=a.batch, device=dev, ddp=world > 1)
+    t.student.train()
+    batch = S.make_batch(a.batch, seed=1234 + rank)
+batch = tuple(v.pin_memory() for v in batch) if a.host else tuple(v.to(dev) for v in batch)
 for _ in range(4):
-    t.step(x, m, th, sync_loss=a.host)
+    t.step(*batch, sync_loss=a.host)
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile
 
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(a.steps):
-        t.step(x, m, th, sync_loss=a.host)
+        t.step(*batch, sync_loss=a.host)
     torch.cuda.synchronize()
 
 if rank == 0:
