@@ -265,6 +265,384 @@ __global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_bwd_kernel(const DecAt
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Tensor-core variant (default): the same two kernels on warp-level mma.sync m16n8k16 bf16 tiles.  The query dimension
+// (T <= 32) is two 16-row tiles, far below a tcgen05 128-row tile, so the legacy warp MMA is the right instrument here:
+// per (sample, head) the contractions are 5 MFLOP backward, and the scalar kernels above were shared-memory-bandwidth
+// bound at one LDS per two FMAs (11 TFLOP/s).  Shared rows are padded by 8 elements (row stride = 16 B mod 128 B) so that
+// every ldmatrix phase touches 8 distinct 16-byte bank groups.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MM_LDK = 72;                  // K / V / Q / dO rows: 64 + 8 bf16
+constexpr int MM_LDP = 264;                 // P~ / dS rows: 256 + 8 bf16
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(ptr)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(ptr)));
+}
+// A tile 16(m) x 16(k) of a row-major matrix S[m][k]
+__device__ __forceinline__ void ld_a(uint32_t (&r)[4], const bf16* S, int ld, int m0, int k0, int lane) {
+  ldsm_x4(r, S + (m0 + (lane & 15)) * ld + k0 + (lane >> 4) * 8);
+}
+// A tile 16(m) x 16(k) of A = X^T where X[k][m] is row-major
+__device__ __forceinline__ void ld_a_t(uint32_t (&r)[4], const bf16* X, int ld, int k0, int m0, int lane) {
+  const int mi = lane >> 3;
+  ldsm_x4_t(r, X + (k0 + (lane & 7) + (mi >> 1) * 8) * ld + m0 + (mi & 1) * 8);
+}
+// B for two n-tiles (n0 .. n0+15) x 16(k) from Y[n][k] row-major: r[0],r[1] = n-tile 0; r[2],r[3] = n-tile 1
+__device__ __forceinline__ void ld_b_nk(uint32_t (&r)[4], const bf16* Y, int ld, int n0, int k0, int lane) {
+  const int mi = lane >> 3;
+  ldsm_x4(r, Y + (n0 + (lane & 7) + (mi >> 1) * 8) * ld + k0 + (mi & 1) * 8);
+}
+// B for two n-tiles (n0 .. n0+15) x 16(k) from Z[k][n] row-major
+__device__ __forceinline__ void ld_b_kn(uint32_t (&r)[4], const bf16* Z, int ld, int k0, int n0, int lane) {
+  const int mi = lane >> 3;
+  ldsm_x4_t(r, Z + (k0 + (lane & 7) + (mi & 1) * 8) * ld + n0 + (mi >> 1) * 8);
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// rows x 64 bf16 from global (ld elements apart) -> shared rows of MM_LDK elements; rows [rows, rows_pad) are zero-filled
+__device__ __forceinline__ void stage_rows_mm(bf16* dst, const bf16* src, int rows, int rows_pad, int ld, int tid) {
+  for (int i = tid; i < rows_pad * 8; i += DA_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) val = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + c * 8);
+    *reinterpret_cast<uint4*>(dst + r * MM_LDK + c * 8) = val;
+  }
+}
+__device__ __forceinline__ bool key_visible(const DecAttnParams& p, int n, int row, int key) {
+  if (row >= p.tq || key >= p.tk) return false;
+  if (p.trg == nullptr) return true;
+  return key <= row && p.trg[(size_t)n * p.tq + key] != (long long)p.pad_idx;
+}
+
+// S fragments of this warp's 32 keys (keys kb .. kb+31) for all 32 query rows: acc[mt][nt][4]
+__device__ __forceinline__ void qk_block(float (&acc)[2][4][4], const bf16* sA, const bf16* sB, int kb, int lane) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a0[4], a1[4];
+    ld_a(a0, sA, MM_LDK, 0, ks * 16, lane);
+    ld_a(a1, sA, MM_LDK, 16, ks * 16, lane);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b[4];
+      ld_b_nk(b, sB, MM_LDK, kb + np * 16, ks * 16, lane);
+      mma_bf16(acc[0][2 * np], a0, b[0], b[1]);
+      mma_bf16(acc[0][2 * np + 1], a0, b[2], b[3]);
+      mma_bf16(acc[1][2 * np], a1, b[0], b[1]);
+      mma_bf16(acc[1][2 * np + 1], a1, b[2], b[3]);
+    }
+  }
+}
+
+// forward.  dynamic shared memory: K [tkp][72] | V [tkp][72] | Q [32][72] | P~ [32][264] (bf16) | red [8][32] f32 | stat [32] f32
+__global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_fwd_mma_kernel(const DecAttnParams p) {
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  const int tkp = (p.tk + 31) & ~31;
+  bf16* sK = reinterpret_cast<bf16*>(da_smem);
+  bf16* sV = sK + tkp * MM_LDK;
+  bf16* sQ = sV + tkp * MM_LDK;
+  bf16* sP = sQ + 32 * MM_LDK;
+  float* sRed = reinterpret_cast<float*>(sP + 32 * MM_LDP);
+  float* sStat = sRed + DA_WARPS * 32;
+  const int n = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_rows_mm(sK, p.k + (size_t)n * p.tk * p.ldk + h * DA_D, p.tk, tkp, p.ldk, threadIdx.x);
+  stage_rows_mm(sV, p.v + (size_t)n * p.tk * p.ldv + h * DA_D, p.tk, tkp, p.ldv, threadIdx.x);
+  stage_rows_mm(sQ, p.q + (size_t)n * p.tq * p.ldq + h * DA_D, p.tq, 32, p.ldq, threadIdx.x);
+  __syncthreads();
+  const uint32_t thresh = drop_threshold(p.p_drop);
+  const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
+  const int kb = warp * 32;
+  const bool active = kb < p.tk;
+  const int r0 = lane >> 2, c0 = 2 * (lane & 3);
+  float acc[2][4][4];
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // rows r0, r0+8, r0+16, r0+24
+  if (active) {
+    qk_block(acc, sQ, sK, kb, lane);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = mt * 16 + r0 + (e >> 1) * 8, key = kb + nt * 8 + c0 + (e & 1);
+          const float s = key_visible(p, n, row, key) ? acc[mt][nt][e] * p.scale : -INFINITY;
+          acc[mt][nt][e] = s;
+          mx[mt * 2 + (e >> 1)] = fmaxf(mx[mt * 2 + (e >> 1)], s);
+        }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+    if ((lane & 3) == 0) sRed[warp * 32 + r0 + 8 * i] = mx[i];
+  }
+  __syncthreads();
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < DA_WARPS; ++w) m = fmaxf(m, sRed[w * 32 + r0 + 8 * i]);
+    mx[i] = m;
+  }
+  __syncthreads();                                                // sRed is reused for the sums
+  if (active) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = mt * 2 + (e >> 1);
+          const float s = acc[mt][nt][e];
+          const float pr = (s == -INFINITY) ? 0.f : __expf(s - mx[i]);
+          acc[mt][nt][e] = pr;
+          sum[i] += pr;
+        }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+    if ((lane & 3) == 0) sRed[warp * 32 + r0 + 8 * i] = sum[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < DA_WARPS; ++w) t += sRed[w * 32 + r0 + 8 * i];
+    sum[i] = t;
+  }
+  if (warp == 0 && (lane & 3) == 0 && p.lse != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = r0 + 8 * i;
+      if (row < p.tq) p.lse[((size_t)n * p.heads + h) * p.tq + row] = mx[i] + __logf(sum[i]);
+    }
+  }
+  if (active) {                                                   // P~ (dropout applied) -> shared, bf16
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int i = mt * 2 + hf, row = mt * 16 + r0 + hf * 8, key = kb + nt * 8 + c0;
+          const float inv = sum[i] > 0.f ? 1.0f / sum[i] : 0.f;
+          float p0 = acc[mt][nt][2 * hf] * inv, p1 = acc[mt][nt][2 * hf + 1] * inv;
+          if (p.p_drop > 0.f) {
+            const unsigned long long idx = (((unsigned long long)blockIdx.x * p.tq + row) << 8) + key;
+            p0 = keep_elem(p.seed, idx, thresh) ? p0 * inv_keep : 0.f;
+            p1 = keep_elem(p.seed, idx + 1, thresh) ? p1 * inv_keep : 0.f;
+          }
+          *reinterpret_cast<uint32_t*>(sP + row * MM_LDP + key) = pack_bf16x2(p0, p1);
+        }
+  }
+  __syncthreads();
+  // O[32 x 64] = P~[32 x tkp] V[tkp x 64]: warp -> (row tile, 16 output columns)
+  {
+    const int mt = warp & 1, n0 = (warp >> 1) * 16;
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int kk = 0; kk < tkp; kk += 16) {
+      uint32_t a[4], b[4];
+      ld_a(a, sP, MM_LDP, mt * 16, kk, lane);
+      ld_b_kn(b, sV, MM_LDK, kk, n0, lane);
+      mma_bf16(o[0], a, b[0], b[1]);
+      mma_bf16(o[1], a, b[2], b[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int row = mt * 16 + r0 + hf * 8;
+        if (row < p.tq)
+          *reinterpret_cast<uint32_t*>(p.o + ((size_t)n * p.tq + row) * p.ldo + h * DA_D + n0 + t * 8 + c0) = pack_bf16x2(o[t][2 * hf], o[t][2 * hf + 1]);
+      }
+  }
+}
+
+// backward.  dynamic shared memory: K [tkp][72] | V [tkp][72] (later P~ | dS [32][264] each) | Q [32][72] | dO [32][72] | lse, delta [32] f32
+__global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_bwd_mma_kernel(const DecAttnParams p) {
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  const int tkp = (p.tk + 31) & ~31;
+  bf16* sK = reinterpret_cast<bf16*>(da_smem);
+  bf16* sV = sK + tkp * MM_LDK;
+  const int v_elems = max(tkp * MM_LDK, 2 * 32 * MM_LDP);        // the V region is reused for P~ and dS
+  bf16* sQ = sV + v_elems;
+  bf16* sDO = sQ + 32 * MM_LDK;
+  float* sLse = reinterpret_cast<float*>(sDO + 32 * MM_LDK);
+  float* sDelta = sLse + 32;
+  bf16* sP = sV;
+  bf16* sDS = sV + 32 * MM_LDP;
+  const int n = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_rows_mm(sK, p.k + (size_t)n * p.tk * p.ldk + h * DA_D, p.tk, tkp, p.ldk, threadIdx.x);
+  stage_rows_mm(sV, p.v + (size_t)n * p.tk * p.ldv + h * DA_D, p.tk, tkp, p.ldv, threadIdx.x);
+  stage_rows_mm(sQ, p.q + (size_t)n * p.tq * p.ldq + h * DA_D, p.tq, 32, p.ldq, threadIdx.x);
+  stage_rows_mm(sDO, p.d_o + (size_t)n * p.tq * p.ldo + h * DA_D, p.tq, 32, p.ldo, threadIdx.x);
+  for (int row = warp; row < 32; row += DA_WARPS) {               // delta_i = dO_i . O_i ; lse_i
+    float d = 0.f;
+    if (row < p.tq) {
+      const size_t off = ((size_t)n * p.tq + row) * p.ldo + h * DA_D;
+      const uint32_t ud = reinterpret_cast<const uint32_t*>(p.d_o + off)[lane];
+      const uint32_t uo = reinterpret_cast<const uint32_t*>(p.o + off)[lane];
+      d = bf16lo(ud) * bf16lo(uo) + bf16hi(ud) * bf16hi(uo);
+    }
+    d = warp_sum(d);
+    if (lane == 0) {
+      sDelta[row] = d;
+      sLse[row] = row < p.tq ? p.lse[((size_t)n * p.heads + h) * p.tq + row] : 0.f;
+    }
+  }
+  __syncthreads();
+  const uint32_t thresh = drop_threshold(p.p_drop);
+  const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
+  const int kb = warp * 32;
+  const bool active = kb < p.tk;
+  const int r0 = lane >> 2, c0 = 2 * (lane & 3);
+  uint32_t pk[2][4][2], dk_[2][4][2];                             // packed bf16 pairs of P~ and dS for this warp's 32 keys
+  if (active) {
+    float acc[2][4][4];
+    float pr[2][4][4];
+    qk_block(acc, sQ, sK, kb, lane);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = mt * 16 + r0 + (e >> 1) * 8, key = kb + nt * 8 + c0 + (e & 1);
+          pr[mt][nt][e] = key_visible(p, n, row, key) ? __expf(acc[mt][nt][e] * p.scale - sLse[row]) : 0.f;
+        }
+    qk_block(acc, sDO, sV, kb, lane);                             // d(P~) = dO V^T
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int row = mt * 16 + r0 + hf * 8, key = kb + nt * 8 + c0;
+          float pt[2], ds[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pe = pr[mt][nt][2 * hf + e];
+            float dp = acc[mt][nt][2 * hf + e];
+            pt[e] = pe;
+            if (p.p_drop > 0.f) {
+              const unsigned long long idx = (((unsigned long long)blockIdx.x * p.tq + row) << 8) + key + e;
+              const bool kp = keep_elem(p.seed, idx, thresh);
+              pt[e] = kp ? pe * inv_keep : 0.f;
+              dp = kp ? dp * inv_keep : 0.f;
+            }
+            ds[e] = pe * (dp - sDelta[row]);
+          }
+          pk[mt][nt][hf] = pack_bf16x2(pt[0], pt[1]);
+          dk_[mt][nt][hf] = pack_bf16x2(ds[0], ds[1]);
+        }
+  }
+  __syncthreads();                                                // every warp is done reading V: its region becomes P~ | dS
+  if (active) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int row = mt * 16 + r0 + hf * 8, key = kb + nt * 8 + c0;
+          *reinterpret_cast<uint32_t*>(sP + row * MM_LDP + key) = pk[mt][nt][hf];
+          *reinterpret_cast<uint32_t*>(sDS + row * MM_LDP + key) = dk_[mt][nt][hf];
+        }
+  }
+  __syncthreads();
+  // dQ[32 x 64] = scale * dS[32 x tkp] K[tkp x 64]: warp -> (row tile, 16 output columns)
+  {
+    const int mt = warp & 1, n0 = (warp >> 1) * 16;
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int kk = 0; kk < tkp; kk += 16) {
+      uint32_t a[4], b[4];
+      ld_a(a, sDS, MM_LDP, mt * 16, kk, lane);
+      ld_b_kn(b, sK, MM_LDK, kk, n0, lane);
+      mma_bf16(o[0], a, b[0], b[1]);
+      mma_bf16(o[1], a, b[2], b[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int row = mt * 16 + r0 + hf * 8;
+        if (row < p.tq)
+          *reinterpret_cast<uint32_t*>(p.dq + ((size_t)n * p.tq + row) * p.lddq + h * DA_D + n0 + t * 8 + c0) =
+              pack_bf16x2(o[t][2 * hf] * p.scale, o[t][2 * hf + 1] * p.scale);
+      }
+  }
+  // dV[keys x 64] = P~^T dO ; dK[keys x 64] = scale * dS^T Q: warp -> its 32 keys (two 16-key tiles), all 64 columns
+  if (active) {
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const bf16* sA = which == 0 ? sP : sDS;
+      const bf16* sB = which == 0 ? sDO : sQ;
+      bf16* dst = which == 0 ? p.dv : p.dk;
+      const int ldd = which == 0 ? p.lddv : p.lddk;
+      const float sc = which == 0 ? 1.0f : p.scale;
+#pragma unroll 1
+      for (int kt = 0; kt < 2; ++kt) {
+        const int key0 = kb + kt * 16;
+        if (key0 >= p.tk) break;
+        float o[8][4];
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[t][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t a[4];
+          ld_a_t(a, sA, MM_LDP, ks * 16, key0, lane);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            ld_b_kn(b, sB, MM_LDK, ks * 16, np * 16, lane);
+            mma_bf16(o[2 * np], a, b[0], b[1]);
+            mma_bf16(o[2 * np + 1], a, b[2], b[3]);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int key = key0 + r0 + hf * 8;
+            if (key < p.tk)
+              *reinterpret_cast<uint32_t*>(dst + ((size_t)n * p.tk + key) * ldd + h * DA_D + t * 8 + c0) =
+                  pack_bf16x2(o[t][2 * hf] * sc, o[t][2 * hf + 1] * sc);
+          }
+      }
+    }
+  }
+}
+
+static size_t dec_attn_mma_smem(int tk, bool bwd) {
+  const int tkp = (tk + 31) & ~31;
+  if (!bwd) return (size_t)(2 * tkp * MM_LDK + 32 * MM_LDK + 32 * MM_LDP) * 2 + (size_t)(DA_WARPS * 32 + 32) * 4;
+  const int v_elems = tkp * MM_LDK > 2 * 32 * MM_LDP ? tkp * MM_LDK : 2 * 32 * MM_LDP;
+  return (size_t)(tkp * MM_LDK + v_elems + 2 * 32 * MM_LDK) * 2 + 64 * 4;
+}
+
+static int g_dec_attn_variant = 1;          // 1 = mma.sync tensor-core kernels (default), 0 = scalar CUDA-core kernels
+
+// ---------------------------------------------------------------------------------------------------------
 // TFLoss: one warp per (sample, position) row of logits [N*T, ld] (first C columns valid)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tf_ce_kernel(const float* __restrict__ logits, int ld, int C, const long long* __restrict__ targets,
@@ -337,13 +715,14 @@ extern "C" int ccd_dec_attn_fwd(const void* q, int ldq, const void* k, int ldk, 
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.ldq = ldq; p.ldk = ldk; p.ldv = ldv;
   p.o = (bf16*)o; p.ldo = ldo; p.lse = lse; p.trg = trg; p.pad_idx = pad_idx;
   p.n = n; p.heads = heads; p.tq = tq; p.tk = tk; p.scale = 0.125f; p.p_drop = p_drop; p.seed = seed;
-  const size_t smem = dec_attn_smem(tq, tk, false);
   static bool attr = false;
   if (!attr) {
     CCD_CUDA_CHECK(cudaFuncSetAttribute(dec_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_attn_smem(DA_MAX_TQ, DA_MAX_TK, false)));
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(dec_attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_attn_mma_smem(DA_MAX_TK, false)));
     attr = true;
   }
-  dec_attn_fwd_kernel<<<n * heads, DA_THREADS, smem, stream>>>(p);
+  if (g_dec_attn_variant == 1) dec_attn_fwd_mma_kernel<<<n * heads, DA_THREADS, dec_attn_mma_smem(tk, false), stream>>>(p);
+  else dec_attn_fwd_kernel<<<n * heads, DA_THREADS, dec_attn_smem(tq, tk, false), stream>>>(p);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }
@@ -365,13 +744,14 @@ extern "C" int ccd_dec_attn_bwd(const void* q, int ldq, const void* k, int ldk, 
   p.o = (bf16*)const_cast<void*>(o); p.ldo = ldo; p.lse = const_cast<float*>(lse); p.trg = trg; p.pad_idx = pad_idx;
   p.n = n; p.heads = heads; p.tq = tq; p.tk = tk; p.scale = 0.125f; p.p_drop = p_drop; p.seed = seed;
   p.d_o = (const bf16*)d_o; p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
-  const size_t smem = dec_attn_smem(tq, tk, true);
   static bool attr = false;
   if (!attr) {
     CCD_CUDA_CHECK(cudaFuncSetAttribute(dec_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_attn_smem(DA_MAX_TQ, DA_MAX_TK, true)));
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(dec_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_attn_mma_smem(DA_MAX_TK, true)));
     attr = true;
   }
-  dec_attn_bwd_kernel<<<n * heads, DA_THREADS, smem, stream>>>(p);
+  if (g_dec_attn_variant == 1) dec_attn_bwd_mma_kernel<<<n * heads, DA_THREADS, dec_attn_mma_smem(tk, true), stream>>>(p);
+  else dec_attn_bwd_kernel<<<n * heads, DA_THREADS, dec_attn_smem(tq, tk, true), stream>>>(p);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }
@@ -396,5 +776,11 @@ extern "C" int ccd_dropout(const void* x, int x_is_bf16, const float* resid, voi
   else if (out_is_bf16) dropout_kernel<float, bf16><<<grid, 256, 0, stream>>>((const float*)x, resid, (bf16*)out, un, p, seed);
   else dropout_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)x, resid, (float*)out, un, p, seed);
   CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+// A/B switch: 1 = mma.sync tensor-core decoder attention (default), 0 = scalar CUDA-core kernels
+extern "C" int ccd_set_dec_attn_variant(int v) {
+  g_dec_attn_variant = v ? 1 : 0;
   return CCD_OK;
 }

@@ -536,6 +536,12 @@ def dec_attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, n, heads, tq, tk, trg=None, p
           int(seed), _s())
 
 
+def set_dec_attn_variant(v):
+    """1 = tensor-core (mma.sync) decoder attention kernels (default), 0 = scalar kernels (A/B switch)."""
+    _bind()
+    _FN["ccd_set_dec_attn_variant"](int(v))
+
+
 def tf_ce(logits, n_classes, targets, pad_idx):
     """logits f32 [n*t, ld]; returns (acc [2] = loss sum, counted rows; dlogits f32 [n*t, ld] = softmax - onehot)."""
     n, t = targets.shape

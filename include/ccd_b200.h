@@ -171,6 +171,9 @@ int ccd_dec_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void*
                      const float* lse, const long long* trg, int pad_idx, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
                      int n, int heads, int tq, int tk, float p_drop, unsigned long long seed, void* stream);
 
+/* A/B switch (process-global): 1 = warp-MMA (mma.sync m16n8k16) decoder attention kernels [default], 0 = scalar CUDA-core kernels */
+int ccd_set_dec_attn_variant(int v);
+
 /* TFLoss (Dino/loss/ce_loss.py:94-128): cross-entropy of logits[:, :-1] against targets[:, 1:], pad_idx ignored.
  * logits f32 [n*t, ld] (first n_classes columns valid); acc_zeroed[0] += sum of row losses, acc_zeroed[1] += counted rows
  * (loss = acc[0] / acc[1]); dlogits f32 [n*t, ld] = softmax - onehot on counted rows, 0 elsewhere (scale by g / acc[1]). */

@@ -24,6 +24,14 @@ def ops():
     return o
 
 
+@pytest.fixture(params=[1, 0], ids=["mma", "scalar"])
+def attn_variant(ops, request):
+    """Both implementations of the decoder attention: warp-MMA tensor-core kernels (default) and the scalar kernels."""
+    ops.set_dec_attn_variant(request.param)
+    yield request.param
+    ops.set_dec_attn_variant(1)
+
+
 def _bf(t):
     return t.to(torch.bfloat16)
 
@@ -44,8 +52,9 @@ def _attn_ref(q, k, v, n, h, tq, tk, mask):
     return (p @ vf).transpose(1, 2).reshape(n * tq, h * 64), p
 
 
-@pytest.mark.parametrize("kind,n,tq,tk", [("self", 5, 25, 25), ("self", 3, 26, 26), ("cross", 4, 25, 256), ("cross", 2, 7, 64)])
-def test_dec_attn_fwd_bwd(ops, kind, n, tq, tk):
+@pytest.mark.parametrize("kind,n,tq,tk", [("self", 5, 25, 25), ("self", 3, 26, 26), ("self", 2, 1, 1), ("cross", 4, 25, 256),
+                                          ("cross", 2, 7, 64), ("cross", 3, 32, 100)])
+def test_dec_attn_fwd_bwd(ops, kind, n, tq, tk, attn_variant):
     from ccd_b200 import synthetic as S
     h = 8
     g = torch.Generator(device="cuda").manual_seed(tq * 31 + tk)
@@ -53,7 +62,7 @@ def test_dec_attn_fwd_bwd(ops, kind, n, tq, tk):
     if kind == "self":
         qkv = _bf(torch.randn(n * tq, 3 * 512, device="cuda", generator=g)).requires_grad_(True)
         q, k, v = qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]
-        trg = S.make_targets(n, seed=3, max_seq_len=tq).cuda()
+        trg = (S.make_targets(n, seed=3, max_seq_len=tq) if tq >= 3 else torch.full((n, tq), 91, dtype=torch.long)).cuda()
         pad = (trg != PAD).unsqueeze(-2)
         sub = torch.tril(torch.ones(tq, tq, device="cuda")).bool().unsqueeze(0)
         mask = (pad & sub).unsqueeze(1)
@@ -82,7 +91,7 @@ def test_dec_attn_fwd_bwd(ops, kind, n, tq, tk):
         assert _rel(dkv.float(), kv_all.grad.float()[:, 1024:2048]) < 1.5e-2
 
 
-def test_dec_attn_dropout_mask_is_replayed(ops):
+def test_dec_attn_dropout_mask_is_replayed(ops, attn_variant):
     """V = identity exposes the dropped probabilities: entries are 0 or P/(1-p), the keep rate is 1-p, and the backward
     uses the very same mask (gradients equal autograd's through the recovered mask)."""
     n, h, tq, tk, p = 6, 8, 25, 64, 0.3
