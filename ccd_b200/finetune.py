@@ -7,7 +7,8 @@ Drop-in for `DINO_Finetune` (Dino/model/dino_vision.py:135-290), `NRTRDecoder` (
 load), same forward signatures and outputs -- but every contraction is a tcgen05 GEMM of libccd_b200.so with a fused
 epilogue (GELU, residual add, GELU'), the decoder's attentions are one fused kernel per (sample, head) whose probabilities
 never reach HBM, the 12 cross-attention K/V projections of the 6 layers are ONE GEMM over the encoder memory, and the
-greedy `forward_test` projects the encoder memory once instead of once per decoding step.
+greedy `forward_test` projects the encoder memory once and decodes incrementally with a per-layer key / value cache
+instead of re-running the whole decoder at every step.
 
   img [N,3,32,128] -> VisionTransformer (ccd_b200.encoder) -> Mlp E->512->512 -> memory bf16 [N*256, 512]
   targets [N,T] -> embedding + sinusoid table -> 6 x (LN -> masked self-attention -> +res -> LN -> cross-attention -> +res
@@ -477,22 +478,54 @@ class NRTRDecoder(nn.Module):
         return logits.view(n, t, -1)[:, :, : self.classifier.weight.shape[0]], None
 
     @torch.no_grad()
-    def forward_test(self, feat, out_enc, img_metas=None, test_speed=False):
-        """Greedy decoding (nrtr_decoder.py:154-203): per-step softmax [N, max_seq_len, 92].  The encoder memory is
-        projected once; each step re-runs the (tiny) decoder on the growing sequence like the reference."""
+    def forward_test(self, feat, out_enc, img_metas=None, test_speed=False, kv_cache=True):
+        """Greedy decoding (nrtr_decoder.py:154-203): per-step softmax [N, max_seq_len, 92].
+        The reference re-runs the whole decoder on the growing (PAD-filled) sequence at every step -- O(T^2) decoder passes of
+        which only row `step` is used.  Causal + pad masking makes the hidden states of earlier positions independent of later
+        tokens, so here (kv_cache=True) every step pushes ONE new token per sample through the layers, appending its
+        self-attention key / value to a per-layer cache; the cross-attention K / V of all layers are projected once.
+        kv_cache=False keeps the reference's schedule (used by the parity test of the cache)."""
         mem = out_enc.reshape(-1, self.d_model)
         n = mem.shape[0] // 256
         wb = self.bf16_weights()
         kv_all = self.project_memory(mem, wb)
-        seq = torch.full((n, self.max_seq_len + 1), self.padding_idx, device=mem.device, dtype=torch.long)
+        T1 = self.max_seq_len + 1
+        seq = torch.full((n, T1), self.padding_idx, device=mem.device, dtype=torch.long)
         seq[:, 0] = self.start_idx
         n_cls = self.classifier.weight.shape[0]
         outputs = []
         was_training = self.training
         self.eval()
+        D = self.d_model
+        if kv_cache:
+            kvs = kv_all.split(2 * D, dim=1)
+            cache = [torch.zeros(n * T1, 3 * D, dtype=torch.bfloat16, device=mem.device) for _ in self.layer_stack]
+            pos = self.position_enc.position_table[0]
         for step in range(self.max_seq_len):
-            hid = self.hidden(seq, kv_all, 256, wb)
-            logits = self.classify(hid, wb).view(n, self.max_seq_len + 1, -1)[:, step, :n_cls]
+            if kv_cache:
+                tok = seq[:, step]
+                x = (F.embedding(tok, self.trg_word_emb.weight, self.padding_idx) + pos[step]).contiguous()      # [N, 512] f32
+                for i, l in enumerate(self.layer_stack):
+                    sa, ca, m = l.self_attn, l.enc_attn, l.mlp
+                    xn = LayerNormFn.apply(x, l.norm1.weight, l.norm1.bias, l.norm1.eps)
+                    qkv = MultiLinearBf16Fn.apply(xn, wb[f"qkv{i}"], None, sa.linear_q.weight, sa.linear_k.weight, sa.linear_v.weight)
+                    c = cache[i].view(n, T1, 3 * D)
+                    c[:, step] = qkv                                                        # keys / values of positions <= step
+                    keys = c[:, : step + 1].reshape(n * (step + 1), 3 * D)                  # every cached token is a real one (PAD is never predicted)
+                    o, _ = ops.dec_attn_fwd(qkv[:, :D], keys[:, D:2 * D], keys[:, 2 * D:], n, N_HEAD, 1, step + 1, None, 0, 0.0, 0,
+                                            want_lse=False)
+                    x = LinearResidFn.apply(o, wb[f"sfc{i}"], sa.fc.weight, None, x, 0.0, 0)
+                    xn = LayerNormFn.apply(x, l.norm2.weight, l.norm2.bias, l.norm2.eps)
+                    q = MultiLinearBf16Fn.apply(xn, wb[f"cq{i}"], None, ca.linear_q.weight)
+                    o, _ = ops.dec_attn_fwd(q, kvs[i][:, :D], kvs[i][:, D:], n, N_HEAD, 1, 256, None, 0, 0.0, 0, want_lse=False)
+                    x = LinearResidFn.apply(o, wb[f"cfc{i}"], ca.fc.weight, None, x, 0.0, 0)
+                    xn = LayerNormFn.apply(x, l.norm3.weight, l.norm3.bias, l.norm3.eps)
+                    x = FFNFn.apply(xn, wb[f"w1{i}"], wb[f"w2{i}"], m.w_1.weight, m.w_1.bias, m.w_2.weight, m.w_2.bias, x, 0.0, 0.0, 0)
+                hid = LayerNormFn.apply(x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
+                logits = self.classify(hid, wb)[:, :n_cls]
+            else:
+                hid = self.hidden(seq, kv_all, 256, wb)
+                logits = self.classify(hid, wb).view(n, T1, -1)[:, step, :n_cls]
             prob = torch.softmax(logits, dim=-1)
             outputs.append(prob)
             seq[:, step + 1] = prob.argmax(dim=-1)

@@ -229,6 +229,27 @@ def test_finetune_greedy_decode_vs_reference_golden():
     assert np.abs(probs.max(-1).values.cpu().numpy()[:, 0] - gold["greedy_maxprob"][:, 0]).max() < 2e-2
 
 
+def test_kv_cached_decoding_equals_full_redecode():
+    """forward_test with the per-layer key/value cache (one new token per step) against the reference's schedule (the whole
+    decoder re-run on the growing sequence at every step), both on the GPU kernels."""
+    arch, model, sd, img, tgt = _build("finetune_vit_small_b3")
+    model.eval()
+    with torch.no_grad():
+        mem = model.encode(img.cuda())
+        a = model.decoder.forward_test(None, mem, kv_cache=True)
+        b = model.decoder.forward_test(None, mem, kv_cache=False)
+    assert a.shape == b.shape == (img.shape[0], 25, 92)
+    aa, bb = a.argmax(-1).cpu().numpy(), b.argmax(-1).cpu().numpy()
+    for i in range(a.shape[0]):                      # identical until a near-tie flips (then the sequences legitimately diverge)
+        for t in range(25):
+            if aa[i, t] != bb[i, t]:
+                top2 = b[i, t].topk(2).values
+                assert (top2[0] - top2[1]).item() < 2e-2, (i, t, top2)
+                break
+            assert (a[i, t] - b[i, t]).abs().max().item() < 2e-2
+    assert (aa[:, 0] == bb[:, 0]).all()
+
+
 def test_finetune_training_mode_runs_with_dropout():
     """train(): dropout (p = 0.1, six places per layer) and drop-path active -- loss finite, every trainable tensor that the
     oracle gives a gradient gets one, two runs with different seeds differ, weights update through the fused optimizer."""
