@@ -27,6 +27,36 @@ enum { CCD_OK = 0, CCD_ERR_ARG = -1, CCD_ERR_CUDA = -2, CCD_ERR_TMAP = -3, CCD_E
 #define CCD_LAUNCH_CHECK() CCD_CUDA_CHECK(cudaGetLastError())
 
 // ---------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The frequently launched kernels of the step (GEMM, LayerNorm, attention) call
+// pdl_launch_dependents() on entry and pdl_wait() before their first global-memory access, and are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs are scheduled onto SMs as they drain and run
+// their prologue (barrier init, TMEM allocation, descriptor prefetch) while the tail of the previous kernel still executes.
+// Both instructions are no-ops for a kernel launched without the attribute; a predecessor that never triggers releases its
+// dependents at completion, i.e. plain stream order.  ccd_set_option(2, 0) launches everything without the attribute.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline int& pdl_enabled() {
+  static int v = 1;
+  return v;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // shared-memory address / mbarrier
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -511,6 +511,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
+  pdl_launch_dependents();
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -519,6 +520,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // operands / auxiliary tensors of the previous kernel are complete and visible
 
   if (warp == 0 || warp == 2) {
     // ===================== TMA producers: warp 0 streams A, warp 2 streams B, continuously over all items =====================
@@ -896,8 +898,8 @@ static int launch_gemm_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB
   wk.n_tiles = wk.n_tiles_n * ((p.M + GEMM_BM - 1) / GEMM_BM);
   wk.n_items = wk.n_tiles * splits;
   const int grid = wk.n_items < num_sms ? wk.n_items : num_sms;
-  gemm_umma_persistent_kernel<EPI, BN, SPATIAL><<<grid, PG_THREADS, PgCfg<BN>::SMEM, stream>>>(tmA, tmB, p, wk, cs);
-  CCD_LAUNCH_CHECK();
+  CCD_CUDA_CHECK(launch_pdl(gemm_umma_persistent_kernel<EPI, BN, SPATIAL>, dim3(grid), dim3(PG_THREADS), (size_t)PgCfg<BN>::SMEM, stream, tmA,
+                            tmB, p, wk, cs));
   return CCD_OK;
 }
 
@@ -1085,9 +1087,11 @@ extern "C" int ccd_conv_gemm(const void* sp, const void* other, int M, int N, in
 }
 
 // debug / A-B switch: key 0 = GEMM variant (1 persistent, 0 one-tile-per-CTA); key 1 = epilogue of full tiles
-// (1 per-shape choice [default], 0 shared-memory transpose, 2 transpose-free thread-per-row wherever alignment allows)
+// (1 per-shape choice [default], 0 shared-memory transpose, 2 transpose-free thread-per-row wherever alignment allows);
+// key 2 = programmatic dependent launch of the GEMM / LayerNorm / attention kernels (1 on [default], 0 off)
 extern "C" int ccd_set_option(int key, int value) {
   if (key == 0) { g_gemm_variant = value ? 1 : 0; return CCD_OK; }
   if (key == 1) { g_gemm_epilogue = (value < 0 || value > 2) ? 1 : value; return CCD_OK; }
+  if (key == 2) { pdl_enabled() = value ? 1 : 0; return CCD_OK; }
   return CCD_ERR_ARG;
 }

@@ -85,6 +85,8 @@ __device__ __forceinline__ void store_tmem_row64(uint32_t taddr, bf16* dst) {
 __global__ void __launch_bounds__(256) mhsa_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o,
                                                          float* __restrict__ delta, const float* __restrict__ lse2,
                                                          float* __restrict__ nlse, float scale, int T, int E, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= T) return;
@@ -406,6 +408,7 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     tma_prefetch_desc(&tmDO);
   }
   float* csum = reinterpret_cast<float*>(smem + L::OFF_CSUM);
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) csum[i] = 0.f;
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
@@ -416,6 +419,7 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tDK = tmem_base + 256, tDV = tmem_base + 320, tDQ = tmem_base + 384;
+  pdl_wait();                                      // delta / lse vectors and dO of the preceding kernels are complete and visible
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -640,8 +644,8 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
   const bool pipelined = g_mhsa_bwd_variant == 1;
   float* nlse_ws = pipelined ? delta_ws + (size_t)S * H * ATB_N : nullptr;      // second half of the workspace
   p.nlse = nlse_ws;
-  mhsa_delta_kernel<<<(S * ATB_N + 7) / 8, 256, 0, stream>>>(p.o, p.d_o, delta_ws, lse2, nlse_ws, p.scale, S * ATB_N, E, H);
-  CCD_LAUNCH_CHECK();
+  CCD_CUDA_CHECK(launch_pdl(mhsa_delta_kernel, dim3((S * ATB_N + 7) / 8), dim3(256), 0, stream, p.o, p.d_o, delta_ws, lse2, nlse_ws, p.scale,
+                            S * ATB_N, E, H));
   if (g_mhsa_bwd_variant == 1) {
     static bool attr2_set = false;
     static int num_sms = 148;
@@ -654,9 +658,8 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
       attr2_set = true;
     }
     const int n_items = S * H;
-    mhsa_bwd_pipelined_kernel<<<n_items < num_sms ? n_items : num_sms, ATB_THREADS, MhsaBwd2Smem::SMEM_BYTES, stream>>>(
-        tmQKV, tmDO, p, n_items);
-    CCD_LAUNCH_CHECK();
+    CCD_CUDA_CHECK(launch_pdl(mhsa_bwd_pipelined_kernel, dim3(n_items < num_sms ? n_items : num_sms), dim3(ATB_THREADS),
+                              (size_t)MhsaBwd2Smem::SMEM_BYTES, stream, tmQKV, tmDO, p, n_items));
     return CCD_OK;
   }
   dim3 grid(H, S);

@@ -271,6 +271,7 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
   }
+  pdl_launch_dependents();
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -279,6 +280,7 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // qkv of the preceding GEMM is complete and visible
 
   if (warp == 0) {
     if (lane == 0) {
@@ -467,8 +469,7 @@ static int launch_mhsa_fwd_persistent(const CUtensorMap& tm, const MhsaFwdParams
   }
   const int n_items = S * p.H;
   const int grid = n_items < num_sms ? n_items : num_sms;
-  mhsa_fwd_persistent_kernel<<<grid, ATT2_THREADS, ATT2_SMEM, stream>>>(tm, p, n_items);
-  CCD_LAUNCH_CHECK();
+  CCD_CUDA_CHECK(launch_pdl(mhsa_fwd_persistent_kernel, dim3(grid), dim3(ATT2_THREADS), (size_t)ATT2_SMEM, stream, tm, p, n_items));
   return CCD_OK;
 }
 

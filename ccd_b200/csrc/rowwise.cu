@@ -14,6 +14,8 @@ constexpr int LN_MAX_V4 = 4;  // E <= 512 -> at most 4 float4 per lane
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, bf16* __restrict__ y_bf16,
                                                             float* __restrict__ y_f32, int rows, int E, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -107,8 +109,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const float* __re
   const int warps_total = gridDim.x * 8;
   const int nv = E >> 2;
   float* my = ln_acc + (size_t)wib * 3 * E;
+  pdl_launch_dependents();
   for (int i = lane; i < 3 * E; i += 32) my[i] = 0.f;
   __syncwarp();
+  pdl_wait();
   float4 gm[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -399,8 +403,8 @@ extern "C" int ccd_layernorm_fwd(const float* x, const float* gamma, const float
                                  int rows, int E, float eps, void* stream) {
   if (!x || !gamma || !beta || rows <= 0 || E <= 0 || (E & 3) || E > 512) return CCD_ERR_ARG;
   const int blocks = (rows + 7) / 8;
-  layernorm_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, (bf16*)y_bf16, y_f32, rows, E, eps);
-  CCD_LAUNCH_CHECK();
+  CCD_CUDA_CHECK(launch_pdl(layernorm_fwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, gamma, beta, (bf16*)y_bf16, y_f32,
+                            rows, E, eps));
   return CCD_OK;
 }
 
@@ -416,9 +420,8 @@ static int launch_ln_bwd(const float* x, const float* gamma, const void* dy, con
   }
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 2) blocks = 148 * 2;          // two resident CTAs per SM, each warp strides over its rows
-  layernorm_bwd_kernel<DY_BF16, NV><<<blocks, 256, smem, stream>>>(x, gamma, dy, resid, dx_f32, (bf16*)dx_bf16, dgamma, dbeta,
-                                                                  bf16_seq_scale, dbias_next, rows, E, eps);
-  CCD_LAUNCH_CHECK();
+  CCD_CUDA_CHECK(launch_pdl(layernorm_bwd_kernel<DY_BF16, NV>, dim3(blocks), dim3(256), (size_t)smem, stream, x, gamma, dy, resid, dx_f32,
+                            (bf16*)dx_bf16, dgamma, dbeta, bf16_seq_scale, dbias_next, rows, E, eps));
   return CCD_OK;
 }
 

@@ -13,15 +13,22 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--arch", default="vit_small")
 ap.add_argument("--mode", default="list")
+ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"])
 a = ap.parse_args()
-t = PretrainStep(arch=a.arch, batch_per_gpu=a.batch, device=torch.device("cuda", 0))
-t.student.train()
-x, m, th = [v.cuda() for v in S.make_batch(a.batch, seed=1234)]
+if a.workload == "finetune":
+    from ccd_b200.trainer import FinetuneStep
+    t = FinetuneStep(arch=a.arch, batch_per_gpu=a.batch, device=torch.device("cuda", 0))
+    t.model.train()
+    batch = (torch.randn(a.batch, 3, 32, 128, generator=torch.Generator().manual_seed(1234)).cuda(), S.make_targets(a.batch, seed=1234).cuda())
+else:
+    t = PretrainStep(arch=a.arch, batch_per_gpu=a.batch, device=torch.device("cuda", 0))
+    t.student.train()
+    batch = tuple(v.cuda() for v in S.make_batch(a.batch, seed=1234))
 for _ in range(2):
-    t.step(x, m, th, sync_loss=False)
+    t.step(*batch, sync_loss=False)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-t.step(x, m, th, sync_loss=False)
+t.step(*batch, sync_loss=False)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("profiled one step, batch", a.batch)
