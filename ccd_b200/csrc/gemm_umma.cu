@@ -1088,7 +1088,7 @@ extern "C" int ccd_conv_gemm(const void* sp, const void* other, int M, int N, in
 
 // debug / A-B switch: key 0 = GEMM variant (1 persistent, 0 one-tile-per-CTA); key 1 = epilogue of full tiles
 // (1 per-shape choice [default], 0 shared-memory transpose, 2 transpose-free thread-per-row wherever alignment allows);
-// key 2 = programmatic dependent launch of the GEMM / LayerNorm / attention kernels (1 on [default], 0 off)
+// key 2 = programmatic dependent launch of the GEMM / LayerNorm / attention kernels (0 off [default], 1 on)
 extern "C" int ccd_set_option(int key, int value) {
   if (key == 0) { g_gemm_variant = value ? 1 : 0; return CCD_OK; }
   if (key == 1) { g_gemm_epilogue = (value < 0 || value > 2) ? 1 : value; return CCD_OK; }

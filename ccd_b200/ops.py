@@ -49,7 +49,7 @@ def _bind():
         _FN["ccd_set_option"](0, int(os.environ["CCD_GEMM_VARIANT"]))
     if "CCD_GEMM_EPILOGUE" in os.environ:           # debug A/B switch (1 = per-shape [default], 0 = smem transpose, 2 = thread-per-row)
         _FN["ccd_set_option"](1, int(os.environ["CCD_GEMM_EPILOGUE"]))
-    if "CCD_PDL" in os.environ:                     # debug A/B switch: programmatic dependent launch (1 = on [default], 0 = off)
+    if "CCD_PDL" in os.environ:                     # debug A/B switch: programmatic dependent launch (0 = off [default], 1 = on)
         _FN["ccd_set_option"](2, int(os.environ["CCD_PDL"]))
     if "CCD_MHSA_BWD_VARIANT" in os.environ:        # 1 = pipelined persistent [default], 0 = first version
         _FN["ccd_set_mhsa_bwd_variant"](int(os.environ["CCD_MHSA_BWD_VARIANT"]))
