@@ -306,14 +306,22 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// rows x 64 bf16 from global (ld elements apart) -> shared rows of MM_LDK elements; rows [rows, rows_pad) are zero-filled
+// rows x 64 bf16 from global (ld elements apart) -> shared rows of MM_LDK elements; rows [rows, rows_pad) are zero-filled.
+// Asynchronous 16-byte copies (LDGSTS): a thread has all of its chunks of K, V, Q (and dO) in flight at once instead of one
+// load -> store round trip per chunk; stage_commit_wait() precedes the __syncthreads that publishes the tiles.
 __device__ __forceinline__ void stage_rows_mm(bf16* dst, const bf16* src, int rows, int rows_pad, int ld, int tid) {
   for (int i = tid; i < rows_pad * 8; i += DA_THREADS) {
     const int r = i >> 3, c = i & 7;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows) val = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + c * 8);
-    *reinterpret_cast<uint4*>(dst + r * MM_LDK + c * 8) = val;
+    bf16* d = dst + r * MM_LDK + c * 8;
+    if (r < rows) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d)), "l"(src + (size_t)r * ld + c * 8) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
+}
+__device__ __forceinline__ void stage_commit_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ bool key_visible(const DecAttnParams& p, int n, int row, int key) {
   if (row >= p.tq || key >= p.tk) return false;
@@ -361,6 +369,7 @@ __global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_fwd_mma_kernel(const D
   stage_rows_mm(sK, p.k + (size_t)n * p.tk * p.ldk + h * DA_D, p.tk, tkp, p.ldk, threadIdx.x);
   stage_rows_mm(sV, p.v + (size_t)n * p.tk * p.ldv + h * DA_D, p.tk, tkp, p.ldv, threadIdx.x);
   stage_rows_mm(sQ, p.q + (size_t)n * p.tq * p.ldq + h * DA_D, p.tq, 32, p.ldq, threadIdx.x);
+  stage_commit_wait();
   __syncthreads();
   const uint32_t thresh = drop_threshold(p.p_drop);
   const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
@@ -508,6 +517,7 @@ __global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_bwd_mma_kernel(const D
       sLse[row] = row < p.tq ? p.lse[((size_t)n * p.heads + h) * p.tq + row] : 0.f;
     }
   }
+  stage_commit_wait();
   __syncthreads();
   const uint32_t thresh = drop_threshold(p.p_drop);
   const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
@@ -633,6 +643,235 @@ __global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_bwd_mma_kernel(const D
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Self-attention over <= 32 target tokens: one WARP per head, one CTA per sample (8 heads).  With one CTA per (sample, head)
+// the 4096 tiny CTAs of a batch-512 launch were launch-bound (87 us forward / 151 us backward for 0.2 GFLOP); here a warp owns
+// its head end to end -- staging (cp.async), S = QK^T, softmax (quad shuffles only), P~V, and in the backward dP, dS, dQ, dV, dK --
+// with no block-level barrier at all.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MM_LDS = 40;                  // P~ / dS rows of the warp-per-head kernels: 32 + 8 bf16
+constexpr int SW_FWD_BYTES = (3 * 32 * MM_LDK + 32 * MM_LDS) * 2;                    // K, V, Q, P~
+constexpr int SW_BWD_BYTES = (4 * 32 * MM_LDK + 2 * 32 * MM_LDS) * 2 + 64 * 4;       // K, V, Q, dO, P~, dS, lse, delta
+
+__device__ __forceinline__ void stage_rows_warp(bf16* dst, const bf16* src, int rows, int ld, int lane) {
+  for (int i = lane; i < 32 * 8; i += 32) {
+    const int r = i >> 3, c = i & 7;
+    bf16* d = dst + r * MM_LDK + c * 8;
+    if (r < rows) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d)), "l"(src + (size_t)r * ld + c * 8) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// C[16*MT... ] helper: out[32 x 64] (two row tiles) = A[32 x 32] B[32 x 64] with A row-major (ld_a) or transposed (ld_a_t), B = Z[k][n]
+template <bool A_T>
+__device__ __forceinline__ void small_mm(float (&o)[8][4], const bf16* sA, int m0, const bf16* sB, int lane) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[t][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t a[4];
+    if (A_T) ld_a_t(a, sA, MM_LDS, ks * 16, m0, lane);
+    else     ld_a(a, sA, MM_LDS, m0, ks * 16, lane);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ld_b_kn(b, sB, MM_LDK, ks * 16, np * 16, lane);
+      mma_bf16(o[2 * np], a, b[0], b[1]);
+      mma_bf16(o[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+__device__ __forceinline__ void store_tile_rows(bf16* dst, int ld, int row0, int n_rows, const float (&o)[8][4], float sc, int lane) {
+  const int r0 = lane >> 2, c0 = 2 * (lane & 3);
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int row = row0 + r0 + hf * 8;
+      if (row < n_rows) *reinterpret_cast<uint32_t*>(dst + (size_t)row * ld + t * 8 + c0) = pack_bf16x2(o[t][2 * hf] * sc, o[t][2 * hf + 1] * sc);
+    }
+}
+
+__global__ void __launch_bounds__(DA_THREADS, 1) dec_self_attn_fwd_warp_kernel(const DecAttnParams p) {
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  const int n = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (h >= p.heads) return;
+  bf16* sK = reinterpret_cast<bf16*>(da_smem + (size_t)h * SW_FWD_BYTES);
+  bf16* sV = sK + 32 * MM_LDK;
+  bf16* sQ = sV + 32 * MM_LDK;
+  bf16* sP = sQ + 32 * MM_LDK;
+  stage_rows_warp(sK, p.k + (size_t)n * p.tk * p.ldk + h * DA_D, p.tk, p.ldk, lane);
+  stage_rows_warp(sV, p.v + (size_t)n * p.tk * p.ldv + h * DA_D, p.tk, p.ldv, lane);
+  stage_rows_warp(sQ, p.q + (size_t)n * p.tq * p.ldq + h * DA_D, p.tq, p.ldq, lane);
+  stage_commit_wait();
+  __syncwarp();
+  const uint32_t thresh = drop_threshold(p.p_drop);
+  const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
+  const int r0 = lane >> 2, c0 = 2 * (lane & 3);
+  const unsigned long long bh = (unsigned long long)n * p.heads + h;
+  float acc[2][4][4];
+  qk_block(acc, sQ, sK, 0, lane);
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = mt * 16 + r0 + (e >> 1) * 8, key = nt * 8 + c0 + (e & 1);
+        const float sc = key_visible(p, n, row, key) ? acc[mt][nt][e] * p.scale : -INFINITY;
+        acc[mt][nt][e] = sc;
+        mx[mt * 2 + (e >> 1)] = fmaxf(mx[mt * 2 + (e >> 1)], sc);
+      }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = mt * 2 + (e >> 1);
+        const float sc = acc[mt][nt][e];
+        const float pr = (sc == -INFINITY) ? 0.f : __expf(sc - mx[i]);
+        acc[mt][nt][e] = pr;
+        sum[i] += pr;
+      }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+    const int row = r0 + 8 * i;
+    if ((lane & 3) == 0 && row < p.tq && p.lse != nullptr) p.lse[(bh)*p.tq + row] = mx[i] + __logf(sum[i]);
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int i = mt * 2 + hf, row = mt * 16 + r0 + hf * 8, key = nt * 8 + c0;
+        const float inv = sum[i] > 0.f ? 1.0f / sum[i] : 0.f;
+        float p0 = acc[mt][nt][2 * hf] * inv, p1 = acc[mt][nt][2 * hf + 1] * inv;
+        if (p.p_drop > 0.f) {
+          const unsigned long long idx = ((bh * p.tq + row) << 8) + key;
+          p0 = keep_elem(p.seed, idx, thresh) ? p0 * inv_keep : 0.f;
+          p1 = keep_elem(p.seed, idx + 1, thresh) ? p1 * inv_keep : 0.f;
+        }
+        *reinterpret_cast<uint32_t*>(sP + row * MM_LDS + key) = pack_bf16x2(p0, p1);
+      }
+  __syncwarp();
+  bf16* obase = p.o + (size_t)n * p.tq * p.ldo + h * DA_D;
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    float o[8][4];
+    small_mm<false>(o, sP, mt * 16, sV, lane);
+    store_tile_rows(obase, p.ldo, mt * 16, p.tq, o, 1.0f, lane);
+  }
+}
+
+__global__ void __launch_bounds__(DA_THREADS, 1) dec_self_attn_bwd_warp_kernel(const DecAttnParams p) {
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  const int n = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (h >= p.heads) return;
+  bf16* sK = reinterpret_cast<bf16*>(da_smem + (size_t)h * SW_BWD_BYTES);
+  bf16* sV = sK + 32 * MM_LDK;
+  bf16* sQ = sV + 32 * MM_LDK;
+  bf16* sDO = sQ + 32 * MM_LDK;
+  bf16* sP = sDO + 32 * MM_LDK;
+  bf16* sDS = sP + 32 * MM_LDS;
+  float* sLse = reinterpret_cast<float*>(sDS + 32 * MM_LDS);
+  float* sDelta = sLse + 32;
+  stage_rows_warp(sK, p.k + (size_t)n * p.tk * p.ldk + h * DA_D, p.tk, p.ldk, lane);
+  stage_rows_warp(sV, p.v + (size_t)n * p.tk * p.ldv + h * DA_D, p.tk, p.ldv, lane);
+  stage_rows_warp(sQ, p.q + (size_t)n * p.tq * p.ldq + h * DA_D, p.tq, p.ldq, lane);
+  stage_rows_warp(sDO, p.d_o + (size_t)n * p.tq * p.ldo + h * DA_D, p.tq, p.ldo, lane);
+  const unsigned long long bh = (unsigned long long)n * p.heads + h;
+  {                                                               // lane = query row: delta_i = dO_i . O_i, lse_i
+    float d = 0.f, l = 0.f;
+    if (lane < p.tq) {
+      const size_t off = ((size_t)n * p.tq + lane) * p.ldo + h * DA_D;
+      const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + off);
+      const uint4* po = reinterpret_cast<const uint4*>(p.o + off);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 a = __ldg(pd + c), b = __ldg(po + c);
+        d += bf16lo(a.x) * bf16lo(b.x) + bf16hi(a.x) * bf16hi(b.x) + bf16lo(a.y) * bf16lo(b.y) + bf16hi(a.y) * bf16hi(b.y) +
+             bf16lo(a.z) * bf16lo(b.z) + bf16hi(a.z) * bf16hi(b.z) + bf16lo(a.w) * bf16lo(b.w) + bf16hi(a.w) * bf16hi(b.w);
+      }
+      l = p.lse[bh * p.tq + lane];
+    }
+    sDelta[lane] = d;
+    sLse[lane] = l;
+  }
+  stage_commit_wait();
+  __syncwarp();
+  const uint32_t thresh = drop_threshold(p.p_drop);
+  const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
+  const int r0 = lane >> 2, c0 = 2 * (lane & 3);
+  {
+    float acc[2][4][4], pr[2][4][4];
+    qk_block(acc, sQ, sK, 0, lane);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = mt * 16 + r0 + (e >> 1) * 8, key = nt * 8 + c0 + (e & 1);
+          pr[mt][nt][e] = key_visible(p, n, row, key) ? __expf(acc[mt][nt][e] * p.scale - sLse[row]) : 0.f;
+        }
+    qk_block(acc, sDO, sV, 0, lane);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int row = mt * 16 + r0 + hf * 8, key = nt * 8 + c0;
+          float pt[2], ds[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pe = pr[mt][nt][2 * hf + e];
+            float dp = acc[mt][nt][2 * hf + e];
+            pt[e] = pe;
+            if (p.p_drop > 0.f) {
+              const unsigned long long idx = ((bh * p.tq + row) << 8) + key + e;
+              const bool kp = keep_elem(p.seed, idx, thresh);
+              pt[e] = kp ? pe * inv_keep : 0.f;
+              dp = kp ? dp * inv_keep : 0.f;
+            }
+            ds[e] = pe * (dp - sDelta[row]);
+          }
+          *reinterpret_cast<uint32_t*>(sP + row * MM_LDS + key) = pack_bf16x2(pt[0], pt[1]);
+          *reinterpret_cast<uint32_t*>(sDS + row * MM_LDS + key) = pack_bf16x2(ds[0], ds[1]);
+        }
+  }
+  __syncwarp();
+  float o[8][4];
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {                                // dQ = scale * dS K
+    small_mm<false>(o, sDS, mt * 16, sK, lane);
+    store_tile_rows(p.dq + (size_t)n * p.tq * p.lddq + h * DA_D, p.lddq, mt * 16, p.tq, o, p.scale, lane);
+  }
+#pragma unroll 1
+  for (int kt = 0; kt < 2; ++kt) {                                // dV = P~^T dO ; dK = scale * dS^T Q
+    if (kt * 16 >= p.tk) break;
+    small_mm<true>(o, sP, kt * 16, sDO, lane);
+    store_tile_rows(p.dv + (size_t)n * p.tk * p.lddv + h * DA_D, p.lddv, kt * 16, p.tk, o, 1.0f, lane);
+    small_mm<true>(o, sDS, kt * 16, sQ, lane);
+    store_tile_rows(p.dk + (size_t)n * p.tk * p.lddk + h * DA_D, p.lddk, kt * 16, p.tk, o, p.scale, lane);
+  }
+}
+
 static size_t dec_attn_mma_smem(int tk, bool bwd) {
   const int tkp = (tk + 31) & ~31;
   if (!bwd) return (size_t)(2 * tkp * MM_LDK + 32 * MM_LDK + 32 * MM_LDP) * 2 + (size_t)(DA_WARPS * 32 + 32) * 4;
@@ -721,7 +960,14 @@ extern "C" int ccd_dec_attn_fwd(const void* q, int ldq, const void* k, int ldk, 
     CCD_CUDA_CHECK(cudaFuncSetAttribute(dec_attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_attn_mma_smem(DA_MAX_TK, false)));
     attr = true;
   }
-  if (g_dec_attn_variant == 1) dec_attn_fwd_mma_kernel<<<n * heads, DA_THREADS, dec_attn_mma_smem(tk, false), stream>>>(p);
+  static bool attr_w = false;
+  if (!attr_w) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(dec_self_attn_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_WARPS * SW_FWD_BYTES));
+    attr_w = true;
+  }
+  if (g_dec_attn_variant == 1 && tk <= 32 && tq <= 32 && heads <= DA_WARPS)
+    dec_self_attn_fwd_warp_kernel<<<n, DA_THREADS, DA_WARPS * SW_FWD_BYTES, stream>>>(p);
+  else if (g_dec_attn_variant == 1) dec_attn_fwd_mma_kernel<<<n * heads, DA_THREADS, dec_attn_mma_smem(tk, false), stream>>>(p);
   else dec_attn_fwd_kernel<<<n * heads, DA_THREADS, dec_attn_smem(tq, tk, false), stream>>>(p);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
@@ -750,7 +996,14 @@ extern "C" int ccd_dec_attn_bwd(const void* q, int ldq, const void* k, int ldk, 
     CCD_CUDA_CHECK(cudaFuncSetAttribute(dec_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_attn_mma_smem(DA_MAX_TK, true)));
     attr = true;
   }
-  if (g_dec_attn_variant == 1) dec_attn_bwd_mma_kernel<<<n * heads, DA_THREADS, dec_attn_mma_smem(tk, true), stream>>>(p);
+  static bool attr_w = false;
+  if (!attr_w) {
+    CCD_CUDA_CHECK(cudaFuncSetAttribute(dec_self_attn_bwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_WARPS * SW_BWD_BYTES));
+    attr_w = true;
+  }
+  if (g_dec_attn_variant == 1 && tk <= 32 && tq <= 32 && heads <= DA_WARPS)
+    dec_self_attn_bwd_warp_kernel<<<n, DA_THREADS, DA_WARPS * SW_BWD_BYTES, stream>>>(p);
+  else if (g_dec_attn_variant == 1) dec_attn_bwd_mma_kernel<<<n * heads, DA_THREADS, dec_attn_mma_smem(tk, true), stream>>>(p);
   else dec_attn_bwd_kernel<<<n * heads, DA_THREADS, dec_attn_smem(tq, tk, true), stream>>>(p);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
