@@ -274,14 +274,6 @@ __global__ void __launch_bounds__(DA_THREADS, 2) dec_attn_bwd_kernel(const DecAt
 constexpr int MM_LDK = 72;                  // K / V / Q / dO rows: 64 + 8 bf16
 constexpr int MM_LDP = 264;                 // P~ / dS rows: 256 + 8 bf16
 
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* ptr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(ptr)));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* ptr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(ptr)));
-}
 // A tile 16(m) x 16(k) of a row-major matrix S[m][k]
 __device__ __forceinline__ void ld_a(uint32_t (&r)[4], const bf16* S, int ld, int m0, int k0, int lane) {
   ldsm_x4(r, S + (m0 + (lane & 15)) * ld + k0 + (lane >> 4) * 8);
@@ -300,11 +292,6 @@ __device__ __forceinline__ void ld_b_nk(uint32_t (&r)[4], const bf16* Y, int ld,
 __device__ __forceinline__ void ld_b_kn(uint32_t (&r)[4], const bf16* Z, int ld, int k0, int n0, int lane) {
   const int mi = lane >> 3;
   ldsm_x4_t(r, Z + (k0 + (lane & 7) + (mi & 1) * 8) * ld + n0 + (mi >> 1) * 8);
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // rows x 64 bf16 from global (ld elements apart) -> shared rows of MM_LDK elements; rows [rows, rows_pad) are zero-filled.
 // Asynchronous 16-byte copies (LDGSTS): a thread has all of its chunks of K, V, Q (and dO) in flight at once instead of one

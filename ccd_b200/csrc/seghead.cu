@@ -235,8 +235,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, 
 
 // ---------------------------------------------------------------------------------------------------------
 // cls: Conv2d(128 -> 2, 3x3, pad 1) on the [n,32,128,128] bf16 feature map (segmentor.py:88,94).  Two output channels
-// cannot feed a tensor-core tile (a 128-wide UMMA tile would waste 98 % of its MACs), so forward, data gradient and
-// weight gradient are CUDA-core kernels: one CTA per image row with the three input rows staged in shared memory
+// cannot feed a tcgen05 tile (a 128-wide UMMA tile would waste 98 % of its MACs).  First version (kept as variant 0): forward,
+// data gradient and weight gradient as CUDA-core kernels, one CTA per image row with the three input rows staged in shared memory
 // (pixel pitch 272 B = 256 B + 16 B pad: the per-pixel channel vectors of neighbouring pixels start in different banks).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CLS_W = 128, CLS_H = 32, CLS_C = 128;
@@ -379,6 +379,243 @@ __global__ void __launch_bounds__(256) seg_cls_wgrad_kernel(const bf16* __restri
   if (cp == 0) { atomicAdd(dbias, bs0); atomicAdd(dbias + 1, bs1); }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// cls on warp-level tensor cores (default).  The CUDA-core kernels above are shared-memory-bandwidth bound (one LDS.128
+// per 8 FMAs forward: 660 us for 537 MB of input against an 82 us HBM floor at batch 256).  An m16n8k16 warp MMA has an
+// 8-wide N: the two classes waste 3/4 of it, which costs nothing here.  fp32 operands (weights forward, the logits gradient
+// backward) are split into bf16 hi + lo parts and multiplied in two MMAs, so the results keep fp32-operand accuracy
+// (the activations are bf16 in memory already).  Forward and weight gradient walk blocks of 8 image rows with a 4-slot ring
+// of row buffers: every input row is staged ONCE per block (cp.async, prefetched one row ahead) instead of three times.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CLS_PX = CLS_PITCH / 2;                   // pixel pitch in bf16 elements (136)
+constexpr int CLS_RB = 8;                               // image rows per work item
+constexpr int CLS_RING = 4 * CLS_ROW_BYTES;             // 141 440 B
+
+__device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
+  hi = __bfloat162float(__float2bfloat16(v));
+  lo = v - hi;
+}
+__device__ __forceinline__ void cls_zero_borders(uint8_t* ring) {
+  for (int i = threadIdx.x; i < 4 * 2 * (CLS_PITCH / 16); i += blockDim.x) {
+    const int slot = i / (2 * (CLS_PITCH / 16)), rem = i % (2 * (CLS_PITCH / 16));
+    const int side = rem / (CLS_PITCH / 16), ch = rem % (CLS_PITCH / 16);
+    *reinterpret_cast<uint4*>(ring + slot * CLS_ROW_BYTES + (side ? (CLS_W + 1) : 0) * CLS_PITCH + ch * 16) = make_uint4(0, 0, 0, 0);
+  }
+}
+// image row yy of image n -> ring slot (yy + 1) & 3 (zeros when yy is outside the image); one commit group per call
+__device__ __forceinline__ void cls_prefetch_row(uint8_t* ring, const bf16* __restrict__ u2, int n, int yy) {
+  const uint32_t dst = smem_u32(ring + ((yy + 1) & 3) * CLS_ROW_BYTES);
+  const bool ok = yy >= 0 && yy < CLS_H;
+  for (int i = threadIdx.x; i < CLS_W * 16; i += blockDim.x) {
+    const int px = i >> 4, ch = i & 15;
+    const bf16* src = ok ? u2 + (((size_t)n * CLS_H + yy) * CLS_W + px) * CLS_C + ch * 8 : u2;
+    cp_async16(dst + (px + 1) * CLS_PITCH + ch * 16, src, ok ? 16 : 0);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ const bf16* cls_row(const uint8_t* ring, int yy) {
+  return reinterpret_cast<const bf16*>(ring + ((yy + 1) & 3) * CLS_ROW_BYTES);
+}
+
+// forward: warp w = pixels [16w, 16w+16) of the row; B fragments (weights, hi / lo) pre-formed in shared memory per (tap, k-step, lane)
+__global__ void __launch_bounds__(256, 1) seg_cls_fwd_mma_kernel(const bf16* __restrict__ u2, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ logits, int n_items) {
+  extern __shared__ __align__(16) uint8_t cls_smem[];
+  uint8_t* ring = cls_smem;
+  uint2* whi = reinterpret_cast<uint2*>(cls_smem + CLS_RING);          // [9 taps][8 k-steps][32 lanes]
+  uint2* wlo = whi + 9 * 8 * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 9 * 8 * 32; i += blockDim.x) {
+    const int l = i & 31, ks = (i >> 5) & 7, tap = i >> 8;
+    const int o = l >> 2, c = ks * 16 + 2 * (l & 3);
+    float h[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+    if (o < 2) {
+      split_bf16(w[(o * CLS_C + c) * 9 + tap], h[0], lo[0]);
+      split_bf16(w[(o * CLS_C + c + 1) * 9 + tap], h[1], lo[1]);
+      split_bf16(w[(o * CLS_C + c + 8) * 9 + tap], h[2], lo[2]);
+      split_bf16(w[(o * CLS_C + c + 9) * 9 + tap], h[3], lo[3]);
+    }
+    whi[i] = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    wlo[i] = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+  }
+  cls_zero_borders(ring);
+  const float b0 = bias[0], b1 = bias[1];
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int n = item / (CLS_H / CLS_RB), y0 = (item % (CLS_H / CLS_RB)) * CLS_RB;
+    __syncthreads();                                    // the previous item's rows are no longer read
+    cls_prefetch_row(ring, u2, n, y0 - 1);
+    cls_prefetch_row(ring, u2, n, y0);
+    cls_prefetch_row(ring, u2, n, y0 + 1);
+    for (int r = 0; r < CLS_RB; ++r) {
+      const int y = y0 + r;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                                  // rows y-1 .. y+1 visible; row y-2's slot is free
+      if (r + 1 < CLS_RB) cls_prefetch_row(ring, u2, n, y + 2);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        const bf16* rowp = cls_row(ring, y + ky - 1) + (warp * 16 + (lane & 15) + kx) * CLS_PX + (lane >> 4) * 8;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          uint32_t a[4];
+          ldsm_x4(a, rowp + ks * 16);
+          const uint2 bh = whi[(tap * 8 + ks) * 32 + lane], bl = wlo[(tap * 8 + ks) * 32 + lane];
+          mma_bf16(acc, a, bh.x, bh.y);
+          mma_bf16(acc, a, bl.x, bl.y);
+        }
+      }
+      if ((lane & 3) == 0) {
+        const int x = warp * 16 + (lane >> 2);
+        float* out = logits + (((size_t)n * 2) * CLS_H + y) * CLS_W;
+        out[x] = acc[0] + b0;
+        out[(size_t)CLS_H * CLS_W + x] = acc[1] + b1;
+        out[x + 8] = acc[2] + b0;
+        out[(size_t)CLS_H * CLS_W + x + 8] = acc[3] + b1;
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// weight gradient: warp w = channels [16w, 16w+16) for all 9 taps; A = (dl row, hi / lo) as a 16 x 16 tile whose rows 0, 1 are the classes
+__global__ void __launch_bounds__(256, 1) seg_cls_wgrad_mma_kernel(const bf16* __restrict__ u2, const float* __restrict__ dl,
+                                                                   float* __restrict__ dw, float* __restrict__ dbias, int n_items) {
+  extern __shared__ __align__(16) uint8_t cls_smem[];
+  uint8_t* ring = cls_smem;
+  float* dls = reinterpret_cast<float*>(cls_smem + CLS_RING);          // [2 buffers][2 classes][128]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cls_zero_borders(ring);
+  float acc[9][2][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[t][j][e] = 0.f;
+  float bsum = 0.f;
+  const int o_b = threadIdx.x >> 7, x_b = threadIdx.x & 127;           // dl element this thread stages / sums
+  int it = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int n = item / (CLS_H / CLS_RB), y0 = (item % (CLS_H / CLS_RB)) * CLS_RB;
+    __syncthreads();
+    cls_prefetch_row(ring, u2, n, y0 - 1);
+    cls_prefetch_row(ring, u2, n, y0);
+    cls_prefetch_row(ring, u2, n, y0 + 1);
+    for (int r = 0; r < CLS_RB; ++r, ++it) {
+      const int y = y0 + r;
+      float* dcur = dls + (it & 1) * 2 * CLS_W;
+      const float dv = dl[(((size_t)n * 2 + o_b) * CLS_H + y) * CLS_W + x_b];
+      dcur[o_b * CLS_W + x_b] = dv;                     // double buffered: the other buffer may still be read by slower warps
+      bsum += dv;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (r + 1 < CLS_RB) cls_prefetch_row(ring, u2, n, y + 2);
+      uint32_t ah[8][2], al[8][2];                      // a0 / a2 of the 8 pixel k-steps (rows 8..15 of the tile are zero)
+      const int o = lane >> 2;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        float h[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+        if (o < 2) {
+          const float* d = dcur + o * CLS_W + ks * 16 + 2 * (lane & 3);
+          split_bf16(d[0], h[0], lo[0]); split_bf16(d[1], h[1], lo[1]);
+          split_bf16(d[8], h[2], lo[2]); split_bf16(d[9], h[3], lo[3]);
+        }
+        ah[ks][0] = pack_bf16x2(h[0], h[1]); ah[ks][1] = pack_bf16x2(h[2], h[3]);
+        al[ks][0] = pack_bf16x2(lo[0], lo[1]); al[ks][1] = pack_bf16x2(lo[2], lo[3]);
+      }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        const int mi = lane >> 3;
+        const bf16* rowp = cls_row(ring, y + ky - 1) + ((lane & 7) + (mi & 1) * 8 + kx) * CLS_PX + warp * 16 + (mi >> 1) * 8;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          uint32_t b[4];
+          ldsm_x4_t(b, rowp + ks * 16 * CLS_PX);        // B[k = pixel][n = channel]: two channel tiles
+          const uint32_t a_h[4] = {ah[ks][0], 0u, ah[ks][1], 0u}, a_l[4] = {al[ks][0], 0u, al[ks][1], 0u};
+          mma_bf16(acc[tap][0], a_h, b[0], b[1]);
+          mma_bf16(acc[tap][0], a_l, b[0], b[1]);
+          mma_bf16(acc[tap][1], a_h, b[2], b[3]);
+          mma_bf16(acc[tap][1], a_l, b[2], b[3]);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if ((lane >> 2) < 2) {
+    const int o = lane >> 2;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = warp * 16 + j * 8 + 2 * (lane & 3);
+        atomicAdd(dw + (o * CLS_C + c) * 9 + tap, acc[tap][j][0]);
+        atomicAdd(dw + (o * CLS_C + c + 1) * 9 + tap, acc[tap][j][1]);
+      }
+  }
+  bsum = warp_sum(bsum);
+  if (lane == 0) atomicAdd(dbias + (warp >> 2), bsum);
+}
+
+// data gradient: du2[px, c] = sum_k A[px, k] B[k, c], k = (tap, class) (18 -> 32): warp w = pixels [16w, 16w+16), all 128 channels
+__global__ void __launch_bounds__(256) seg_cls_dgrad_mma_kernel(const float* __restrict__ dl, const float* __restrict__ w,
+                                                                bf16* __restrict__ du2) {
+  __shared__ float dls[3][2][CLS_W + 2];
+  __shared__ uint2 wfr[2][16][32];                       // B fragments [k-step][channel tile][lane], bf16 hi part
+  __shared__ uint2 wfl[2][16][32];                       // lo part (w - hi)
+  const int n = blockIdx.x / CLS_H, y = blockIdx.x % CLS_H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * 2 * (CLS_W + 2); i += blockDim.x) {
+    const int r = i / (2 * (CLS_W + 2)), o = (i / (CLS_W + 2)) & 1, xx = i % (CLS_W + 2) - 1;
+    const int yy = y + r - 1;
+    dls[r][o][xx + 1] = (yy >= 0 && yy < CLS_H && xx >= 0 && xx < CLS_W) ? dl[(((size_t)n * 2 + o) * CLS_H + yy) * CLS_W + xx] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 2 * 16 * 32; i += blockDim.x) {
+    const int l = i & 31, nt = (i >> 5) & 15, ks = i >> 9;
+    const int c = nt * 8 + (l >> 2), t0 = ks * 8 + (l & 3), t1 = t0 + 4;
+    const float w00 = t0 < 9 ? w[(0 * CLS_C + c) * 9 + t0] : 0.f, w01 = t0 < 9 ? w[(1 * CLS_C + c) * 9 + t0] : 0.f;
+    const float w10 = t1 < 9 ? w[(0 * CLS_C + c) * 9 + t1] : 0.f, w11 = t1 < 9 ? w[(1 * CLS_C + c) * 9 + t1] : 0.f;
+    float h[4], lo[4];
+    split_bf16(w00, h[0], lo[0]); split_bf16(w01, h[1], lo[1]); split_bf16(w10, h[2], lo[2]); split_bf16(w11, h[3], lo[3]);
+    wfr[ks][nt][l] = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    wfl[ks][nt][l] = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+  }
+  __syncthreads();
+  // A fragments: k pair (2 (lane & 3), +1) = (tap t, class 0 / 1); value = dl[class][y + 1 - ky][x + 1 - kx]
+  uint32_t ah[2][4], al[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int t = ks * 8 + (lane & 3) + (e >> 1) * 4, px = warp * 16 + (lane >> 2) + (e & 1) * 8;
+      float h0 = 0.f, l0 = 0.f, h1 = 0.f, l1 = 0.f;
+      if (t < 9) {
+        const int ky = t / 3, kx = t % 3;
+        split_bf16(dls[2 - ky][0][px + 2 - kx], h0, l0);
+        split_bf16(dls[2 - ky][1][px + 2 - kx], h1, l1);
+      }
+      ah[ks][e] = pack_bf16x2(h0, h1);
+      al[ks][e] = pack_bf16x2(l0, l1);
+    }
+  bf16* orow = du2 + (((size_t)n * CLS_H + y) * CLS_W + warp * 16 + (lane >> 2)) * CLS_C + 2 * (lane & 3);
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint2 b = wfr[ks][nt][lane], bl = wfl[ks][nt][lane];
+      mma_bf16(acc, ah[ks], b.x, b.y);
+      mma_bf16(acc, al[ks], b.x, b.y);
+      mma_bf16(acc, ah[ks], bl.x, bl.y);
+    }
+    *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(acc[0], acc[1]);
+    *reinterpret_cast<uint32_t*>(orow + (size_t)8 * CLS_C + nt * 8) = pack_bf16x2(acc[2], acc[3]);
+  }
+}
+
+static int g_cls_variant = 1;                           // 1 = warp-MMA kernels (default), 0 = CUDA-core kernels
+
 }  // namespace ccd
 
 using namespace ccd;
@@ -450,6 +687,18 @@ extern "C" int ccd_seg_cls_fwd(const void* u2, const float* w, const float* bias
     CCD_CUDA_CHECK(cudaFuncSetAttribute(seg_cls_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
+  if (g_cls_variant == 1) {
+    const int smem2 = CLS_RING + 2 * 9 * 8 * 32 * 8;
+    static bool attr2 = false;
+    if (!attr2) {
+      CCD_CUDA_CHECK(cudaFuncSetAttribute(seg_cls_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr2 = true;
+    }
+    const int items = n_img * (CLS_H / CLS_RB);
+    seg_cls_fwd_mma_kernel<<<items < 148 ? items : 148, 256, smem2, (cudaStream_t)stream>>>((const bf16*)u2, w, bias, logits, items);
+    CCD_LAUNCH_CHECK();
+    return CCD_OK;
+  }
   seg_cls_fwd_kernel<<<n_img * CLS_H, 256, smem, (cudaStream_t)stream>>>((const bf16*)u2, w, bias, logits);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
@@ -457,7 +706,8 @@ extern "C" int ccd_seg_cls_fwd(const void* u2, const float* w, const float* bias
 
 extern "C" int ccd_seg_cls_dgrad(const float* dl, const float* w, void* du2, int n_img, void* stream) {
   if (!dl || !w || !du2 || n_img <= 0) return CCD_ERR_ARG;
-  seg_cls_dgrad_kernel<<<n_img * CLS_H, 256, 0, (cudaStream_t)stream>>>(dl, w, (bf16*)du2);
+  if (g_cls_variant == 1) seg_cls_dgrad_mma_kernel<<<n_img * CLS_H, 256, 0, (cudaStream_t)stream>>>(dl, w, (bf16*)du2);
+  else seg_cls_dgrad_kernel<<<n_img * CLS_H, 256, 0, (cudaStream_t)stream>>>(dl, w, (bf16*)du2);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }
@@ -470,9 +720,27 @@ extern "C" int ccd_seg_cls_wgrad(const void* u2, const float* dl, float* dw_zero
     CCD_CUDA_CHECK(cudaFuncSetAttribute(seg_cls_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
+  if (g_cls_variant == 1) {
+    const int smem2 = CLS_RING + 2 * 2 * CLS_W * 4;
+    static bool attr2 = false;
+    if (!attr2) {
+      CCD_CUDA_CHECK(cudaFuncSetAttribute(seg_cls_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr2 = true;
+    }
+    const int items = n_img * (CLS_H / CLS_RB);
+    seg_cls_wgrad_mma_kernel<<<items < 148 ? items : 148, 256, smem2, (cudaStream_t)stream>>>((const bf16*)u2, dl, dw_zeroed, dbias_zeroed, items);
+    CCD_LAUNCH_CHECK();
+    return CCD_OK;
+  }
   const int rows = n_img * CLS_H;
   const int grid = rows < 296 ? rows : 296;
   seg_cls_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)u2, dl, dw_zeroed, dbias_zeroed, rows);
   CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+// A/B switch: 1 = warp-MMA classifier-convolution kernels (default), 0 = CUDA-core kernels
+extern "C" int ccd_set_seg_cls_variant(int v) {
+  g_cls_variant = v ? 1 : 0;
   return CCD_OK;
 }

@@ -500,6 +500,12 @@ def bn_bwd_apply(dy, lddy, x, ldx, mean, rstd, gamma, beta, sums, inv_m, M, C):
     return dx
 
 
+def set_seg_cls_variant(v):
+    """1 = tensor-core (mma.sync) classifier-convolution kernels (default), 0 = CUDA-core kernels (A/B switch)."""
+    _bind()
+    _FN["ccd_set_seg_cls_variant"](int(v))
+
+
 def seg_cls_fwd(u2, w, bias, n_img):
     logits = torch.empty(n_img, 2, 32, 128, dtype=torch.float32, device=u2.device)
     _call("ccd_seg_cls_fwd", _p(u2), _p(_chk(w, torch.float32)), _p(bias), _p(logits), n_img, _s())

@@ -186,6 +186,9 @@ int ccd_tf_ce(const float* logits, int ld, int n_classes, const long long* targe
 int ccd_dropout(const void* x, int x_is_bf16, const float* resid, void* out, int out_is_bf16, long long n, float p,
                 unsigned long long seed, void* stream);
 
+/* A/B switch (process-global): 1 = warp-MMA (mma.sync) classifier-convolution kernels [default], 0 = CUDA-core kernels */
+int ccd_set_seg_cls_variant(int v);
+
 /* debug / A-B switches (process-global): key 0 = GEMM variant (1 = persistent [default], 0 = one tile per CTA);
    key 1 = epilogue of full tiles in the persistent GEMM (1 = per-shape choice [default], 0 = shared-memory transpose,
    2 = transpose-free thread-per-row wherever alignment allows);

@@ -107,9 +107,19 @@ def test_batchnorm_relu_fwd_bwd(ops):
     assert _rel(dz.float(), zr.grad) < 1e-2
 
 
-@pytest.mark.parametrize("n", [1, 3])
-def test_cls_conv_cuda_core_kernels(ops, n):
-    """cls = Conv2d(128 -> 2, 3x3, pad 1) (segmentor.py:88,94): forward, data and weight/bias gradients against F.conv2d."""
+@pytest.mark.parametrize("variant", [1, 0], ids=["mma", "cuda-core"])
+@pytest.mark.parametrize("n", [1, 3, 40])
+def test_cls_conv_kernels(ops, n, variant):
+    """cls = Conv2d(128 -> 2, 3x3, pad 1) (segmentor.py:88,94): forward, data and weight/bias gradients against F.conv2d
+    in fp64, for the warp-MMA kernels (fp32 operands split into bf16 hi + lo) and the CUDA-core kernels."""
+    ops.set_seg_cls_variant(variant)
+    try:
+        _cls_conv_case(ops, n)
+    finally:
+        ops.set_seg_cls_variant(1)
+
+
+def _cls_conv_case(ops, n):
     g = torch.Generator(device="cuda").manual_seed(n)
     x = torch.randn(n, 128, 32, 128, device="cuda", generator=g).to(torch.bfloat16)
     w = torch.randn(2, 128, 3, 3, device="cuda", generator=g) * 0.05
