@@ -148,12 +148,12 @@ def cpu_reference_arm_finetune(args, as_line):
     from ccd_b200.finetune import DINO_Finetune
     cores = usable_cores()
     torch.set_num_threads(cores)
-    B = max(args.cpu_batch, 8)
+    B = args.cpu_batch
     shapes = {k: v.shape for k, v in DINO_Finetune(S.finetune_config("vit_small")).state_dict().items()}
     sd = {k: v.requires_grad_(v.dtype.is_floating_point and "position_table" not in k) for k, v in S.fill_state_dict(shapes, 0).items()}
     img = torch.randn(B, 3, 32, 128, generator=torch.Generator().manual_seed(1234))
     tgt = S.make_targets(B, seed=1234)
-    steps, warm = (args.steps, args.warmup) if as_line else (2, 1)
+    steps, warm = (args.steps, args.warmup) if as_line else (4, 1)
     budget = float(os.environ.get("CCD_CPU_BUDGET_S", "150" if as_line else "40"))
     times, t_begin = [], time.perf_counter()
     for i in range(warm + steps):
@@ -202,7 +202,7 @@ def cpu_reference_arm(args, as_line):
     tsd = S.fill_state_dict(shapes_t, 0)
     x, masks, metrics = S.make_batch(B, seed=1234)
     center = torch.zeros(1, 65536)
-    steps, warm = (args.steps, args.warmup) if as_line else (2, 1)
+    steps, warm = (args.steps, args.warmup) if as_line else (4, 1)
     times = []
     budget = float(os.environ.get("CCD_CPU_BUDGET_S", "150" if as_line else "40"))
     t_begin = time.perf_counter()
@@ -287,7 +287,7 @@ def main():
                     help="pretrain = BASELINE config 2/3 (the headline metric); finetune = BASELINE config 5 (batch 512)")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--out-dim", type=int, default=65536)
-    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the bounded CPU sample (about 10-30 s of host work in total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write per-shape GEMM/attention timings (json)")
