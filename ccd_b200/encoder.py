@@ -11,7 +11,6 @@ autograd.Function that drives the C-ABI kernels:
                  GELU' fused in the dgrad epilogue, LN backward fused with the residual-gradient add.
 Parameters stay fp32 nn.Parameters; bf16 operand copies are refreshed by one multi-tensor cast per forward.
 """
-import math
 
 import torch
 import torch.nn as nn

@@ -15,7 +15,6 @@ instead of re-running the whole decoder at every step.
                    -> LN -> FFN 512->256->512 -> +res) -> LN -> Linear 512->92 -> TFLoss
 There is no CPU / eager fallback: the modules raise on CPU tensors.
 """
-import math
 
 import numpy as np
 import torch

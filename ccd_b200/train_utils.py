@@ -4,7 +4,6 @@
 host-side restatements so that a training step can be driven without the reference tree, plus the multi-tensor
 teacher EMA on the sm_100a kernel.
 """
-import math
 
 import numpy as np
 import torch

@@ -17,7 +17,6 @@ Pinned against the UNMODIFIED reference executed in the build container (tests/t
 /root/reference) and by the committed fixture tests/golden/finetune_vit_tiny.npz (tests/golden/make_golden_finetune.py).
 Only tests/, __graft_entry__.smoke() and bench.py's reference legs may import this file.
 """
-import math
 
 import numpy as np
 import torch

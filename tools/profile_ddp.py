@@ -1,7 +1,6 @@
 """Phase timing (CUDA events) + torch.profiler kernel table of the pretraining step, with or without DDP.
     python tools/profile_ddp.py                       # 1 GPU
     torchrun --nproc-per-node 2 tools/profile_ddp.py  # DDP"""
-import math
 import os
 import sys
 
