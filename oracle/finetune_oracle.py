@@ -14,7 +14,8 @@ config 5): `DINO_Finetune.forward_train` / `forward_test` of TongkunGuan/CCD (re
 Functional over a flat {name: tensor} state dict with the reference's parameter names; every dropout is the identity
 (the parity configuration: `model.eval()` / p = 0, like drop_path_rate = 0 for the pretraining oracle).
 Pinned against the UNMODIFIED reference executed in the build container (tests/test_finetune_oracle.py, needs
-/root/reference) and by the committed fixture tests/golden/finetune_vit_tiny.npz (tests/golden/make_golden_finetune.py).
+/root/reference) and by the committed fixtures tests/golden/finetune_vit_tiny_b4.npz / finetune_vit_small_b3.npz
+(tests/golden/make_golden_finetune.py).
 Only tests/, __graft_entry__.smoke() and bench.py's reference legs may import this file.
 """
 

@@ -229,6 +229,26 @@ def test_finetune_greedy_decode_vs_reference_golden():
     assert np.abs(probs.max(-1).values.cpu().numpy()[:, 0] - gold["greedy_maxprob"][:, 0]).max() < 2e-2
 
 
+def test_finetune_edge_case_targets_vs_oracle():
+    """Label edge cases of AttnConvertor.str2tensor (convertor/attn.py:87-105): a word truncated to max_seq_len (no EOS, no PAD
+    at all), the shortest word (BOS, one character, EOS, 22 x PAD), a word of one repeated character, an unknown character;
+    odd batch size.  Loss against the oracle on the host; every gradient finite."""
+    import finetune_oracle as FO
+    from ccd_b200.finetune import AttnConvertor
+    arch, model, sd, _, _ = _build("finetune_vit_tiny_b4")
+    conv = AttnConvertor(dict_type="DICT90", max_seq_len=25, with_unknown=True)
+    tgt = conv.str2tensor(["x" * 40, "a", "zzzzzzzz", "caf\u00e9!", "B200"])
+    assert (tgt[0] != PAD).all() and (tgt[1] == PAD).sum() == 22
+    img = torch.randn(5, 3, 32, 128, generator=torch.Generator().manual_seed(77))
+    model.eval()
+    loss, _ = model(img.cuda(), tgt.cuda(), return_loss=True)
+    loss.backward()
+    with torch.no_grad():
+        ref, _, _ = FO.finetune_forward_train(sd, arch, img, tgt)
+    assert abs(loss.item() - ref.item()) <= 1e-3 * abs(ref.item()), (loss.item(), ref.item())
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
 def test_kv_cached_decoding_equals_full_redecode():
     """forward_test with the per-layer key/value cache (one new token per step) against the reference's schedule (the whole
     decoder re-run on the growing sequence at every step), both on the GPU kernels."""
