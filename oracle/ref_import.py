@@ -86,6 +86,12 @@ def load_reference():
     if not reference_available():
         raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
     _install_stubs()
+    try:
+        # first import of torchvision registers torch.library fakes and walks the caller's frames with inspect; do it before
+        # the reference's __file__-less namespace package `Dino` is on the stack (Dino/model/dino_vision.py:9 imports it)
+        import torchvision  # noqa: F401
+    except Exception:
+        pass
     # our own repo ships a `Dino` drop-in package: make sure the reference's wins for this process
     for k in [k for k in sys.modules if k == "Dino" or k.startswith("Dino.")]:
         del sys.modules[k]
