@@ -343,6 +343,34 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 //     shared memory (K-major A of dK, MN-major A of dQ), four 16 KB sub-blocks that are recycled per key tile;
 //   * TMEM: stage 0 [0,128) stage 1 [128,256) | dK [256,320) dV [320,384) dQ_0 [384,448) dQ_1 [448,512).
 // ---------------------------------------------------------------------------------------------------------
+// Diagnostic timeline (tools/att_trace.py; compiled in only with -DCCD_ATT_TRACE=1, never in the product build): CTA 0 appends
+// (role, event, item, sub-tile, clock64) records so that the waiting of every role of the pipelined kernel can be laid out
+// on one time axis.  roles: 0 TMA producer, 1 MMA issuer, 2 / 3 softmax-gradient warpgroup 0 / 1 (lane 0 of its first warp).
+#ifndef CCD_ATT_TRACE
+#define CCD_ATT_TRACE 0
+#endif
+#if CCD_ATT_TRACE
+__device__ long long* g_att_trace_buf = nullptr;
+__device__ unsigned int g_att_trace_n = 0;
+__device__ unsigned int g_att_trace_cap = 0;
+__device__ __forceinline__ void att_trace(int role, int ev, int item, int sub) {
+  if (blockIdx.x != 0 || g_att_trace_buf == nullptr) return;
+  const unsigned int i = atomicAdd(&g_att_trace_n, 1u);
+  if (i < g_att_trace_cap) {
+    long long* r = g_att_trace_buf + 4 * (size_t)i;
+    r[0] = ((long long)role << 32) | (unsigned int)ev;
+    r[1] = item;
+    r[2] = sub;
+    r[3] = clock64();
+  }
+}
+#define ATT_TRACE(role, ev, item, sub) att_trace(role, ev, item, sub)
+#else
+#define ATT_TRACE(role, ev, item, sub) ((void)0)
+#endif
+// events: 1 wait begin / 2 wait end on bar_done (producer) ; 10/11 bar_qk+bar_vdo, 12/13 bar_pd, 14/15 bar_epi, 16 S/dP issued,
+// 17 dV/dK(/dQ) issued (issuer) ; 20/21 bar_free, 22/23 bar_s, 24 math + P/dS written, 25/26 bar_acc, 27 dK/dV/dQ stored (softmax)
+
 struct MhsaBwd2Smem {
   static constexpr int TILE = ATB_N * ATB_D * 2;  // 32 KB
   static constexpr int OFF_Q = 0;
@@ -428,7 +456,9 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int s = w / p.H, h = w - s * p.H;
         const int row0 = s * ATB_N;
+        ATT_TRACE(0, 1, it, 0);
         mbar_wait(bar_done, (it & 1) ^ 1);            // previous item's MMAs no longer read Q/K/V/dO (passes for it = 0)
+        ATT_TRACE(0, 2, it, 0);
         mbar_arrive_expect_tx(bar_qk, 2 * L::TILE + 2048);
         // -lse2 and -delta*scale of the item's 256 queries (pre-formed by mhsa_delta_kernel), double buffered per item
         bulk_load_1d(smem + L::OFF_LSE + (it & 1) * 1024, p.nlse + (size_t)w * ATB_N, 1024, bar_qk);
@@ -468,16 +498,25 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       };
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        ATT_TRACE(1, 10, it, 0);
         mbar_wait(bar_qk, it & 1);
         mbar_wait(bar_vdo, it & 1);
+        ATT_TRACE(1, 11, it, 0);
         tc_fence_after();
         issue_s(0);
         issue_s(1);
+        ATT_TRACE(1, 16, it, 1);
 #pragma unroll 1
         for (int s = 0; s < 8; ++s) {
           const int g = s & 1, j = s >> 2, qs = s & 3;
+          ATT_TRACE(1, 12, it, s);
           mbar_wait(&bar_pd[g], (s >> 1) & 1);
-          if (qs == 0) mbar_wait(bar_epi, j ^ 1);     // dK / dV (dQ) accumulators of the previous key tile / item read out
+          ATT_TRACE(1, 13, it, s);
+          if (qs == 0) {
+            ATT_TRACE(1, 14, it, s);
+            mbar_wait(bar_epi, j ^ 1);                // dK / dV (dQ) accumulators of the previous key tile / item read out
+            ATT_TRACE(1, 15, it, s);
+          }
           tc_fence_after();
           const uint32_t tP = tmem_base + g * 128;    // bf16 P^T over the first 32 columns of the stage
           const uint32_t aDSq = aDS + qs * 16384;
@@ -503,6 +542,7 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           }
           if (qs == 3) umma_commit(bar_acc);
           if (s == 7) umma_commit(bar_done);
+          ATT_TRACE(1, 17, it, s);
           if (s + 2 < 8) issue_s(s + 2);              // overwrites stage g: after the dV MMAs above (in-order) and after
         }                                             // warpgroup g finished reading it (bar_pd)
       }
@@ -527,8 +567,12 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       for (int s = g; s < 8; s += 2) {
         const int j = s >> 2, qs = s & 3;
         const uint32_t tS = tmem_base + g * 128 + lane_sel;
+        const bool tr = (lane == 0 && q4 == ((2 + 4 * g) & 3));      // lane 0 of the warpgroup's first warp
+        if (tr) ATT_TRACE(2 + g, 20, it, s);
         mbar_wait(&bar_free[qs], j ^ 1);              // the dQ / dK MMAs that read this dS^T sub-block have retired
+        if (tr) { ATT_TRACE(2 + g, 21, it, s); ATT_TRACE(2 + g, 22, it, s); }
         mbar_wait(&bar_s[g], (s >> 1) & 1);
+        if (tr) ATT_TRACE(2 + g, 23, it, s);
         tc_fence_after();
         const uint32_t ds_row = sDS + qs * 16384 + r * 128;
 #pragma unroll
@@ -576,10 +620,13 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&bar_pd[g]);
+        if (tr) ATT_TRACE(2 + g, 24, it, s);
         if (qs >= 2) {
           // last sub-tile of this warpgroup in key tile j: once the tile's MMAs retired, write dK_j (warpgroup 0) /
           // dV_j (warpgroup 1); after the second key tile also dQ_0 / dQ_1
+          if (tr) ATT_TRACE(2 + g, 25, it, s);
           mbar_wait(bar_acc, j);
+          if (tr) ATT_TRACE(2 + g, 26, it, s);
           tc_fence_after();
           bf16* drow = p.dqkv + ((size_t)row0 + j * 128 + r) * (3 * p.E) + h * ATB_D;
           const bool want_bias = p.dbias != nullptr;
@@ -591,6 +638,7 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           }
           tc_fence_before();
           mbar_arrive(bar_epi);
+          if (tr) ATT_TRACE(2 + g, 27, it, s);
         }
       }
     }
@@ -673,3 +721,18 @@ extern "C" int ccd_set_mhsa_bwd_variant(int value) {
   g_mhsa_bwd_variant = value ? 1 : 0;
   return CCD_OK;
 }
+
+#if CCD_ATT_TRACE
+// diagnostic builds only (tools/att_trace.py): buf = device buffer of cap records x 4 int64
+extern "C" int ccd_debug_att_trace(long long* buf, unsigned int cap) {
+  const unsigned int zero = 0;
+  CCD_CUDA_CHECK(cudaMemcpyToSymbol(ccd::g_att_trace_buf, &buf, sizeof(buf)));
+  CCD_CUDA_CHECK(cudaMemcpyToSymbol(ccd::g_att_trace_cap, &cap, sizeof(cap)));
+  CCD_CUDA_CHECK(cudaMemcpyToSymbol(ccd::g_att_trace_n, &zero, sizeof(zero)));
+  return CCD_OK;
+}
+extern "C" int ccd_debug_att_trace_count(unsigned int* out) {
+  CCD_CUDA_CHECK(cudaMemcpyFromSymbol(out, ccd::g_att_trace_n, sizeof(unsigned int)));
+  return CCD_OK;
+}
+#endif
