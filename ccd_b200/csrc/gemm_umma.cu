@@ -353,6 +353,33 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //     requested before the transpose).
 // 352 threads: warp 0 TMA(A), warp 1 MMA, warp 2 TMA(B), warps 3-6 epilogue group 0, warps 7-10 epilogue group 1.
 // ---------------------------------------------------------------------------------------------------------
+// Diagnostic timeline (tools/gemm_trace.py; compiled in only with -DCCD_GEMM_TRACE=1, never in the product build): CTA 0 appends
+// (role, event, item, aux, clock64) records.  roles: 0 TMA producer A, 1 MMA issuer, 2 TMA producer B, 3 / 7 first warp of
+// epilogue warpgroup 0 / 1 (lane 0).  events: 1/2 wait begin / end on an empty ring slot (aux = k-block), 10/11 tmem_empty,
+// 12/13 full ring slot (aux = k-block), 14 tile's MMAs issued, 20/21 tmem_full, 22 accumulator handed back, 23 tile stored.
+#ifndef CCD_GEMM_TRACE
+#define CCD_GEMM_TRACE 0
+#endif
+#if CCD_GEMM_TRACE
+__device__ long long* g_gemm_trace_buf = nullptr;
+__device__ unsigned int g_gemm_trace_n = 0;
+__device__ unsigned int g_gemm_trace_cap = 0;
+__device__ __forceinline__ void gemm_trace(int role, int ev, int item, int aux) {
+  if (blockIdx.x != 0 || g_gemm_trace_buf == nullptr) return;
+  const unsigned int i = atomicAdd(&g_gemm_trace_n, 1u);
+  if (i < g_gemm_trace_cap) {
+    long long* r = g_gemm_trace_buf + 4 * (size_t)i;
+    r[0] = ((long long)role << 32) | (unsigned int)ev;
+    r[1] = item;
+    r[2] = aux;
+    r[3] = clock64();
+  }
+}
+#define GEMM_TRACE(role, ev, item, aux) gemm_trace(role, ev, item, aux)
+#else
+#define GEMM_TRACE(role, ev, item, aux) ((void)0)
+#endif
+
 constexpr int PG_THREADS = 352;
 constexpr int PG_STAGING = 32 * 32 * 4;                            // 4 KB per epilogue warp: one 32x32 fp32 chunk
 template <int BN> struct PgCfg {
@@ -535,7 +562,9 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         for (int i = 0; i < nkb; ++i, ++kbc) {
           const int s = kbc % STAGES;
           const uint32_t ph = (kbc / STAGES) & 1;
+          GEMM_TRACE(warp, 1, item, i);
           mbar_wait(&empty_bar[s], ph ^ 1);
+          GEMM_TRACE(warp, 2, item, i);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const int k0 = (kb_begin + i) * GEMM_BK;
@@ -588,13 +617,17 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         const int kb_begin = z * p_in.kb_per_split;
         const int nkb = min(kb_total, kb_begin + p_in.kb_per_split) - kb_begin;
         const int acc = it & 1;
+        GEMM_TRACE(1, 10, item, 0);
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);         // epilogue drained this accumulator
+        GEMM_TRACE(1, 11, item, 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int i = 0; i < nkb; ++i, ++kbc) {
           const int s = kbc % STAGES;
           const uint32_t ph = (kbc / STAGES) & 1;
+          GEMM_TRACE(1, 12, item, i);
           mbar_wait(&full_bar[s], ph);
+          GEMM_TRACE(1, 13, item, i);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
@@ -609,6 +642,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full[acc]);
+        GEMM_TRACE(1, 14, item, 0);
       }
     }
     __syncwarp();
@@ -675,7 +709,9 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           if (p.seq_scale != nullptr) sc = __ldg(p.seq_scale + (row >> 8));
         }
         __syncwarp();
+        if (lane == 0 && q == 3) GEMM_TRACE(warp, 20, item, 1);
         mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+        if (lane == 0 && q == 3) GEMM_TRACE(warp, 21, item, 1);
         tc_fence_after();
 #pragma unroll
         for (int cc = 0; cc < CHUNKS_PER_GROUP; ++cc) {
@@ -697,6 +733,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           if (cc == CHUNKS_PER_GROUP - 1) {      // this group's half of the accumulator is read: hand it back to the MMA issuer
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0 && q == 3) GEMM_TRACE(warp, 22, item, 1);
           }
 #if CCD_DBG_EPI == 3
           if (raw[0] != 0x7fc12345u) continue;
@@ -763,9 +800,12 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           }
         }
         __syncwarp();                            // the bias staging is rewritten for the next tile
+        if (lane == 0 && q == 3) GEMM_TRACE(warp, 23, item, 1);
         continue;
       }
+      if (lane == 0 && q == 3) GEMM_TRACE(warp, 20, item, 0);
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      if (lane == 0 && q == 3) GEMM_TRACE(warp, 21, item, 0);
       tc_fence_after();
       // Full tiles (every row and column valid) take a branch-free path: all eight staging loads of a chunk are issued
       // back to back, then the 32 independent epilogue chains, then the stores.  (The masked path below serialises
@@ -794,6 +834,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           if (c == c_end - 1) {                  // this group's half of the accumulator is read: hand it back to the MMA issuer
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0 && q == 3) GEMM_TRACE(warp, 22, item, 0);
           }
 #if CCD_DBG_EPI == 3
           if (raw[0] != 0x7fc12345u) continue;
@@ -869,6 +910,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         }
         __syncwarp();                            // the 4 KB transpose buffer is rewritten by the next chunk
       }
+      if (lane == 0 && q == 3) GEMM_TRACE(warp, 23, item, 0);
     }
   }
 
@@ -1095,3 +1137,18 @@ extern "C" int ccd_set_option(int key, int value) {
   if (key == 2) { pdl_enabled() = value ? 1 : 0; return CCD_OK; }
   return CCD_ERR_ARG;
 }
+
+#if CCD_GEMM_TRACE
+// diagnostic builds only (tools/gemm_trace.py): buf = device buffer of cap records x 4 int64
+extern "C" int ccd_debug_gemm_trace(long long* buf, unsigned int cap) {
+  const unsigned int zero = 0;
+  CCD_CUDA_CHECK(cudaMemcpyToSymbol(ccd::g_gemm_trace_buf, &buf, sizeof(buf)));
+  CCD_CUDA_CHECK(cudaMemcpyToSymbol(ccd::g_gemm_trace_cap, &cap, sizeof(cap)));
+  CCD_CUDA_CHECK(cudaMemcpyToSymbol(ccd::g_gemm_trace_n, &zero, sizeof(zero)));
+  return CCD_OK;
+}
+extern "C" int ccd_debug_gemm_trace_count(unsigned int* out) {
+  CCD_CUDA_CHECK(cudaMemcpyFromSymbol(out, ccd::g_gemm_trace_n, sizeof(unsigned int)));
+  return CCD_OK;
+}
+#endif
