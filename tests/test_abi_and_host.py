@@ -11,7 +11,7 @@ def test_library_exports_every_declared_symbol():
     from ccd_b200 import lib
     L = lib.load()
     syms = lib.declared_symbols()
-    assert len(syms) >= 29
+    assert len(syms) >= 47
     for s in syms:
         assert hasattr(L, s), s
     assert L.ccd_abi_version() == 1
@@ -28,6 +28,17 @@ def test_argument_validation_without_gpu():
     assert f["ccd_layernorm_fwd"](1, 1, 1, 1, None, 10, 1024, 1e-6, None) == -1                               # E > 512
     assert f["ccd_ccl_label"](1, 7, 1, None, None, 4, None) == -1                                              # bad mode
     assert f["ccd_dino_ce_fwd"](1, 1, 1, 0.1, 0.04, 1, 1, 1, 4, 1001, None) == -1                             # K % 4
+    # recognition decoder entry points
+    assert f["ccd_dec_attn_fwd"](None, 512, None, 512, None, 512, None, 512, None, None, 92, 4, 8, 25, 25, 0.0, 0, None) == -1
+    assert f["ccd_dec_attn_fwd"](16, 512, 16, 512, 16, 512, 16, 512, None, None, 92, 4, 8, 33, 256, 0.0, 0, None) == -1     # tq > 32
+    assert f["ccd_dec_attn_fwd"](16, 512, 16, 512, 16, 512, 16, 512, None, None, 92, 4, 8, 25, 257, 0.0, 0, None) == -1     # tk > 256
+    assert f["ccd_dec_attn_fwd"](16, 512, 16, 512, 16, 512, 16, 512, None, 16, 92, 4, 8, 25, 256, 0.0, 0, None) == -1      # mask needs tk == tq
+    assert f["ccd_dec_attn_fwd"](16, 516, 16, 512, 16, 512, 16, 512, None, None, 92, 4, 8, 25, 25, 0.0, 0, None) == -1      # ld % 8
+    assert f["ccd_dec_attn_fwd"](16, 512, 16, 512, 16, 512, 16, 512, None, None, 92, 4, 8, 25, 25, 1.0, 0, None) == -1      # p_drop < 1
+    assert f["ccd_tf_ce"](16, 90, 92, 16, 4, 25, 92, 16, 16, None) == -1                                       # ld < classes
+    assert f["ccd_tf_ce"](16, 96, 92, 16, 4, 1, 92, 16, 16, None) == -1                                        # T must exceed 1
+    assert f["ccd_dropout"](16, 0, None, 16, 0, 0, 0.1, 0, None) == -1 and f["ccd_dropout"](16, 0, None, 16, 0, 10, 1.5, 0, None) == -1
+    assert f["ccd_set_dec_attn_variant"](1) == 0 and f["ccd_set_seg_cls_variant"](1) == 0
 
 
 def test_no_cpu_fallback():
@@ -42,6 +53,15 @@ def test_no_cpu_fallback():
         ops.layernorm_fwd(torch.zeros(4, 192), torch.ones(192), torch.zeros(192))
     with pytest.raises(NotImplementedError):
         vits.VisionTransformer(patch_size=16, embed_dim=768, num_heads=12, qkv_bias=True)
+    # recognition path: same rule
+    from Dino.decoder.nrtr_decoder import NRTRDecoder
+    from Dino.model.dino_vision import DINO_Finetune
+    from ccd_b200 import synthetic as S
+    ft = DINO_Finetune(S.finetune_config("vit_tiny"))
+    with pytest.raises(RuntimeError):
+        ft(torch.zeros(2, 3, 32, 128), S.make_targets(2), return_loss=True)
+    with pytest.raises(NotImplementedError):
+        NRTRDecoder(d_model=256, d_embedding=256)
 
 
 def test_param_groups_clip_and_schedules():
