@@ -552,7 +552,9 @@ class TFLoss(nn.Module):
         targets = targets_dict['padded_targets'].to(outputs.device)
         n, t, c = outputs.shape
         base = outputs._base if outputs._base is not None else outputs          # the padded [N*T, 96] logits of the decoder
-        if base.dim() == 2 and base.shape[0] == n * t and base.is_contiguous():
+        if (base.dim() == 2 and base.shape[0] == n * t and base.is_contiguous() and base.dtype == torch.float32
+                and outputs.storage_offset() == base.storage_offset()
+                and outputs.stride() == (t * base.shape[1], base.shape[1], 1)):
             flat = base
         else:                                                                   # foreign logits: pad the class dimension to 8
             flat = F.pad(outputs.reshape(n * t, c), (0, (-c) % 8)).contiguous()
