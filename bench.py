@@ -179,56 +179,118 @@ def cpu_reference_arm_finetune(args, as_line):
                       "cpu_baseline": cb, "e2e": {"value": B / sec, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def _time_cpu_steps(step_fn, steps, warm, budget):
+    """Bounded sample: `warm` untimed + up to `steps` timed calls, stopping once `budget` seconds are spent."""
+    times, t_begin = [], time.perf_counter()
+    for i in range(warm + steps):
+        if times and time.perf_counter() - t_begin > budget:
+            break
+        t0 = time.perf_counter()
+        step_fn()
+        if i >= warm or (i == warm - 1 and time.perf_counter() - t_begin > budget):
+            times.append(time.perf_counter() - t0)
+    return times
+
+
 def cpu_reference_arm(args, as_line):
-    """The reference algorithm's own CPU path (oracle/ccd_oracle.py, pinned against the unmodified reference) on the host
-    cores of this box: fwd + loss + bwd of one synthetic batch, fp32, all threads."""
+    """The reference's own CPU path on the host cores of this box: one full pretraining step (train.py:229-272: student fwd,
+    teacher fwd, loss, backward, per-parameter clip, AdamW, EMA, centre) of ViT-Small on one synthetic batch, fp32, all
+    usable threads.  kind = "reference": the UNMODIFIED reference modules from /root/reference or its verbatim, hash-checked
+    copy oracle/_ref (oracle/ref_step.py); kind = "port" (the oracle restatement) only if neither is present."""
     if getattr(args, "workload", "pretrain") == "finetune":
         return cpu_reference_arm_finetune(args, as_line)
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ccd_oracle as O
     from ccd_b200 import synthetic as S
-    from ccd_b200.encoder import vit_small
-    from ccd_b200.head import DINOHead
-    from ccd_b200.model import ABIDINOModel
-    from ccd_b200.segmentor import SegHead
     cores = usable_cores()
     torch.set_num_threads(cores)
     B = args.cpu_batch
-    torch.manual_seed(0)
-    shapes_s = {k: v.shape for k, v in ABIDINOModel(vit_small(patch_size=4), SegHead(in_channels=384), DINOHead(384, 65536)).state_dict().items()}
-    shapes_t = {k: v for k, v in shapes_s.items() if not k.startswith("segmentation.")}
-    ssd = {k: v.requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in S.fill_state_dict(shapes_s, 0).items()}
-    tsd = S.fill_state_dict(shapes_t, 0)
-    x, masks, metrics = S.make_batch(B, seed=1234)
-    center = torch.zeros(1, 65536)
     steps, warm = (args.steps, args.warmup) if as_line else (4, 1)
-    times = []
     budget = float(os.environ.get("CCD_CPU_BUDGET_S", "150" if as_line else "40"))
-    t_begin = time.perf_counter()
-    for i in range(warm + steps):
-        if times and time.perf_counter() - t_begin > budget:       # bounded sample: stop once the time budget is spent
-            break
-        t0 = time.perf_counter()
-        L, parts = O.pretrain_loss(ssd, tsd, "vit_small", x, metrics, masks, center, 0, 0.04)
-        L.backward()
-        for v in ssd.values():
-            v.grad = None
-        center = parts["center"].detach()
-        if i >= warm or (i == warm - 1 and time.perf_counter() - t_begin > budget):
-            times.append(time.perf_counter() - t0)
+    x, masks, metrics = S.make_batch(B, seed=1234)
+    import ref_import
+    if ref_import.reference_available():
+        import warnings
+        warnings.simplefilter("ignore")
+        from ref_step import ReferenceStep
+        torch.manual_seed(0)
+        ref = ReferenceStep("vit_small", out_dim=65536, drop_path_rate=0.1, device="cpu")
+        ref.student.train()
+        times = _time_cpu_steps(lambda: ref.step(x, masks, metrics, 0), steps, warm, budget)
+        kind = "reference"
+        what = (f"UNMODIFIED reference modules ({'oracle/_ref copy' if 'oracle' in ref_import.REFERENCE_ROOT else ref_import.REFERENCE_ROOT}) "
+                "full step fwd+loss+bwd+clip+AdamW+EMA")
+    else:
+        import ccd_oracle as O
+        from ccd_b200.encoder import vit_small
+        from ccd_b200.head import DINOHead
+        from ccd_b200.model import ABIDINOModel
+        from ccd_b200.segmentor import SegHead
+        torch.manual_seed(0)
+        shapes_s = {k: v.shape for k, v in ABIDINOModel(vit_small(patch_size=4), SegHead(in_channels=384), DINOHead(384, 65536)).state_dict().items()}
+        shapes_t = {k: v for k, v in shapes_s.items() if not k.startswith("segmentation.")}
+        ssd = {k: v.requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in S.fill_state_dict(shapes_s, 0).items()}
+        tsd = S.fill_state_dict(shapes_t, 0)
+        state = {"center": torch.zeros(1, 65536)}
+
+        def port_step():
+            L, parts = O.pretrain_loss(ssd, tsd, "vit_small", x, metrics, masks, state["center"], 0, 0.04)
+            L.backward()
+            for v in ssd.values():
+                v.grad = None
+            state["center"] = parts["center"].detach()
+
+        times = _time_cpu_steps(port_step, steps, warm, budget)
+        kind = "port"
+        what = "oracle (fp32 torch restatement of the reference) fwd+loss+bwd"
     sec = sum(times) / len(times)
-    cb = {"value": B / sec, "unit": "images/s", "cores": cores, "kind": "port",
-          "sample": f"oracle (fp32 torch restatement of the reference) ViT-Small fwd+loss+bwd, batch {B}, out_dim 65536, "
-                    f"{len(times)} timed step(s) of {sec:.2f} s"}
+    cb = {"value": B / sec, "unit": "images/s", "cores": cores, "kind": kind,
+          "sample": f"{what}, ViT-Small, batch {B}, out_dim 65536, {len(times)} timed step(s) of {sec:.2f} s"}
     if not as_line:
         return cb
     line = {"metric": METRIC, "value": B / sec, "unit": "images/s", "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "ViT-Small CCD pretrain step (2 views, out_dim 65536), bounded CPU sample", "batch": B},
+            "config": {"workload": "ViT-Small CCD pretrain step (2 views, out_dim 65536, drop_path 0.1), bounded CPU sample", "batch": B},
             "cpu_baseline": cb, "e2e": {"value": B / sec, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def stock_cuda_run(arch, batch, out_dim, iters, warmup, autocast, timeout_s=900, env=None):
+    """the reference's OWN train() (train.py:45-302, unmodified, reference modules: SyncBN convert, teacher DDP,
+    student DDP(find_unused_parameters=True), per-parameter clip, torch AdamW, .data EMA, CPU component labelling) on this box's
+    GPU(s), driven by oracle/run_ref_train.py on synthetic batches.  One process per GPU (inherits RANK/WORLD_SIZE from torchrun)."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_ref_train.py"), "--impl", "reference", "--arch", arch, "--batch", str(batch),
+           "--out_dim", str(out_dim), "--iters", str(iters + warmup), "--warmup", str(warmup), "--autocast", autocast, "--drop_path", "0.1"]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s, env=env)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timeout after {timeout_s} s"}
+    for ln in reversed(r.stdout.splitlines()):
+        if ln.startswith("{"):
+            try:
+                d = json.loads(ln)
+            except Exception:
+                continue
+            if "unavailable" in d:
+                return {"error": d["unavailable"]}
+            return {"images_per_s": d["images_per_s"], "ms_per_step": d["mean_iter_ms"], "steps": iters, "warmup": warmup, "world": d["world"],
+                    "loss_first": d["losses"][0] if d["losses"] else None}
+    return {"error": (r.stderr or r.stdout)[-300:]}
+
+
+def stock_cuda_arm(args):
+    """`--impl stock-cuda`: B1 at N = WORLD_SIZE GPUs, fp32 as shipped (use_fp16: False) and under bf16 autocast."""
+    rank = int(os.environ.get("RANK", "0"))
+    out = {}
+    for mode, ac in (("autocast_bf16", "bf16"), ("fp32", "none")):
+        env = dict(os.environ)
+        env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + (101 if ac == "bf16" else 202))   # own rendezvous per run
+        out[mode] = stock_cuda_run(args.arch, args.batch, args.out_dim, args.steps, max(3, args.warmup), ac, env=env)
+    if rank == 0:
+        print(json.dumps({"impl": "stock-cuda", "metric": METRIC, "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+                          "what": "the reference's own train() + modules on CUDA (BASELINE.md B1), synthetic batches",
+                          "batch_per_gpu": args.batch, "arch": args.arch, "results": out}))
 
 
 def stock_eager_cuda_arm(args):
@@ -279,9 +341,9 @@ def stock_eager_cuda_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ccd_b200", choices=["ccd_b200", "reference", "stock-eager-cuda"])
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ccd_b200", choices=["ccd_b200", "reference", "stock-cuda", "stock-eager-cuda"])
     ap.add_argument("--arch", default="vit_small")
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"],
                     help="pretrain = BASELINE config 2/3 (the headline metric); finetune = BASELINE config 5 (batch 512)")
@@ -290,6 +352,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the bounded CPU sample (about 10-30 s of host work in total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stock-baseline", action="store_true", help="skip the embedded B1 sample (reference train() on this GPU)")
     ap.add_argument("--profile-out", default=None, help="write per-shape GEMM/attention timings (json)")
     args = ap.parse_args()
     finetune = args.workload == "finetune"
@@ -302,6 +365,9 @@ def main():
     if args.impl == "reference":
         if rank == 0:
             cpu_reference_arm(args, as_line=True)
+        return
+    if args.impl == "stock-cuda":
+        stock_cuda_arm(args)
         return
     if args.impl == "stock-eager-cuda":
         if rank == 0:
@@ -323,6 +389,17 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
     B = args.batch
+    # ---- BASELINE.md B1 sample, embedded like cpu_baseline: the reference's own train() + modules on this same GPU, before this
+    # arm allocates anything (N = 1 only; `--impl stock-cuda` under torch.distributed.run measures it at any N)
+    stock = None
+    if world == 1 and not finetune and not args.no_stock_baseline:
+        env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC")}
+        env.update(RANK="0", WORLD_SIZE="1", LOCAL_RANK=str(local), MASTER_ADDR="127.0.0.1")
+        stock = {"what": "reference train() + reference modules on CUDA (train.py:45-302 unmodified via oracle/run_ref_train.py), "
+                         f"{args.arch} batch {B}, out_dim {args.out_dim}, synthetic batches, 1 GPU", "unit": "images/s"}
+        for mode, ac, port in (("autocast_bf16", "bf16", 29711), ("fp32", "none", 29712)):
+            env["MASTER_PORT"] = str(port)
+            stock[mode] = stock_cuda_run(args.arch, B, args.out_dim, int(os.environ.get("CCD_STOCK_STEPS", "8")), 3, ac, timeout_s=600, env=env)
     if finetune:
         trainer = FinetuneStep(arch=args.arch, batch_per_gpu=B, drop_path_rate=0.1, device=dev, ddp=ddp)
         trainer.model.train()
@@ -438,6 +515,8 @@ def main():
         "step_tensor_util": fs * value / world / (peak_tf * 1e12),
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "loss": final_loss,
     }
+    if stock is not None:
+        line["stock_cuda_baseline"] = stock
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_arm(args, as_line=False)
     print(json.dumps(line))

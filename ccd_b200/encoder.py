@@ -138,25 +138,33 @@ class VisionTransformer(nn.Module):
         """(parameter, bf16 operand copy) pairs, for the fused optimizer step that refreshes the copies in its own pass."""
         return list(zip(self._bf16_srcs(), self._bf16)) if self._bf16 is not None else []
 
+    # ---- freshness of the bf16 operand copies -------------------------------------------------------------------------
+    # A tensor's version counter does not see `.data` / raw-pointer / set_ updates (the reference's own teacher EMA is
+    # `param_k.data.mul_(m).add_(...)`, train.py:264-272), so it cannot be the freshness signal.  Rule: EVERY forward
+    # re-casts (one multi-tensor kernel, ~50 us for ViT-Small) unless the fused optimizer step (optim.AdamW), which
+    # rewrites parameter and copy in the same pass, vouched for the copies since the last forward -- a one-shot token.
     def bf16_mark_fresh(self):
         self._bf16_ver = tuple(p._version for p in self._bf16_srcs())
 
+    def bf16_invalidate(self):
+        """Call after modifying GEMM weights behind the fused optimizer's back between its step() and the next forward."""
+        self._bf16_ver = None
+
     def bf16_is_fresh(self):
-        return self._bf16_ver == tuple(p._version for p in self._bf16_srcs())
+        return self._bf16_ver is not None and self._bf16_ver == tuple(p._version for p in self._bf16_srcs())
 
     def _bf16_weights(self):
-        """bf16 operand copies of the GEMM weights: one multi-tensor cast kernel, skipped while the copies are fresh
-        (tensor version counters unchanged since the cast / since the fused optimizer step rewrote them)."""
+        """bf16 operand copies of the GEMM weights: one multi-tensor cast kernel per forward, skipped only when the fused
+        optimizer step rewrote the copies itself (see above)."""
         params = self._bf16_srcs()
         srcs = [p.detach() for p in params]
         if self._bf16 is None or self._bf16[0].device != srcs[0].device:
             self._bf16 = [torch.empty(s.shape, dtype=torch.bfloat16, device=s.device) for s in srcs]
             self._bf16_ver = None
-        ver = tuple(p._version for p in params)
-        if ver != self._bf16_ver:
+        if not self.bf16_is_fresh():
             table, n = self._cast.get(srcs, self._bf16, 2)
             ops.multi_tensor(ops.MT_CAST_BF16, table, n)
-            self._bf16_ver = ver
+        self._bf16_ver = None                                  # one-shot: consumed by this forward
         E = self.embed_dim
         wp = torch.zeros(E, 64, dtype=torch.bfloat16, device=srcs[0].device)     # K padded 48 -> 64
         wp[:, :48] = self.patch_embed.proj.weight.detach().reshape(E, 48)

@@ -18,6 +18,7 @@ There is no CPU / eager fallback: the modules raise on CPU tensors.
 
 import numpy as np
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -382,7 +383,6 @@ class NRTRDecoder(nn.Module):
         self.classifier = nn.Linear(d_model, num_classes - 1)          # PAD is never predicted
         self._cast = ops.ChunkTable()
         self._buf = None
-        self._ver = None
         self._calls = 0
 
     # ---- bf16 operand copies: concatenated where layers share their input; one multi-tensor cast per step ----
@@ -409,24 +409,27 @@ class NRTRDecoder(nn.Module):
                 if name == "cls":
                     rows = (rows + 7) // 8 * 8
                 self._buf[name] = torch.zeros(rows, ws[0].shape[1], dtype=torch.bfloat16, device=dev)
-            self._ver = None
-        ver = tuple(p._version for p in params)
-        if ver != self._ver:
-            srcs, dsts = [], []
-            for name, ws in groups.items():
-                r = 0
-                for w in ws:
-                    srcs.append(w.detach())
-                    dsts.append(self._buf[name][r:r + w.shape[0]])
-                    r += w.shape[0]
-            table, n = self._cast.get(srcs, dsts, 2)
-            ops.multi_tensor(ops.MT_CAST_BF16, table, n)
-            self._ver = ver
+        # re-cast on every forward (one small multi-tensor launch): tensor version counters do not see `.data` / raw-pointer
+        # updates, so they cannot vouch for the copies
+        srcs, dsts = [], []
+        for name, ws in groups.items():
+            r = 0
+            for w in ws:
+                srcs.append(w.detach())
+                dsts.append(self._buf[name][r:r + w.shape[0]])
+                r += w.shape[0]
+        table, n = self._cast.get(srcs, dsts, 2)
+        ops.multi_tensor(ops.MT_CAST_BF16, table, n)
         return self._buf
 
     def _seed(self):
+        """Seed of one dropout site: a fresh draw from torch's CPU generator (so torch.manual_seed / RNG-state restores are
+        honoured and a resumed run does not replay masks) mixed with the rank (DDP ranks hold the same torch seed but must
+        drop independently, as the reference's per-rank CUDA generators do)."""
         self._calls += 1
-        return (torch.initial_seed() * 1000003 + self._calls * 7919) & 0x7FFFFFFFFFFFFFFF
+        draw = int(torch.randint(0, 1 << 62, (1,)).item())
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        return (draw ^ (rank * 0x9E3779B97F4A7C15) ^ (self._calls * 7919)) & 0x7FFFFFFFFFFFFFFF
 
     def project_memory(self, mem, wb):
         """K / V projections of ALL layers' cross-attentions over the encoder memory bf16 [N*256, 512]: one GEMM, N = 12*512."""
@@ -665,19 +668,14 @@ class DINO_Finetune(nn.Module):
                                    start_idx=config.decoder_start_idx, padding_idx=config.decoder_padding_idx)
         self.loss = TFLoss(ignore_index=self.label_convertor.padding_idx)
         self._enc_b16 = None
-        self._enc_ver = None
         self._enc_cast = ops.ChunkTable()
 
     def _encoder_bf16(self):
         ps = [self.encoder.fc1.weight, self.encoder.fc2.weight]
         if self._enc_b16 is None or self._enc_b16[0].device != ps[0].device:
             self._enc_b16 = [torch.empty(p.shape, dtype=torch.bfloat16, device=p.device) for p in ps]
-            self._enc_ver = None
-        ver = tuple(p._version for p in ps)
-        if ver != self._enc_ver:
-            table, n = self._enc_cast.get([p.detach() for p in ps], self._enc_b16, 2)
-            ops.multi_tensor(ops.MT_CAST_BF16, table, n)
-            self._enc_ver = ver
+        table, n = self._enc_cast.get([p.detach() for p in ps], self._enc_b16, 2)      # every forward (see NRTRDecoder.bf16_weights)
+        ops.multi_tensor(ops.MT_CAST_BF16, table, n)
         return self._enc_b16
 
     def extract_feat(self, img):

@@ -7,14 +7,26 @@ Forward/backward are one autograd.Function over the C ABI: tcgen05 GEMMs with bi
 weight-norm scale g/||v|| folded into the bf16 operand copy of the last layer, and (fast path) the bf16 dlogits
 written by the distillation-loss backward consumed directly as the GEMM A operand.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
 from . import ops
 from .encoder import trunc_normal_
 
-# data_ptr of a logits tensor -> bf16 dlogits left there by loss.DinoCEFn.backward (see HeadFn.backward)
-DLOGITS_STASH = {}
+# Hand-off of the bf16 dlogits from the distillation-loss backward to the head backward (no fp32 [2R,K] gradient is ever
+# written).  HeadFn.forward registers the logits it produced (data_ptr -> weak reference to its autograd node; a dead node =
+# a stale entry); loss.DinoCEFn.backward uses the hand-off ONLY for registered logits and returns an ordinary dense
+# gradient for anything else (a foreign head, a clone / slice / scaled view, a leaf tensor in a unit test).
+HEAD_LOGITS = {}          # data_ptr -> (weakref(ctx of HeadFn), shape)
+DLOGITS_STASH = {}        # data_ptr -> (bf16 dlogits, data_ptr of the zero-stride placeholder autograd carries instead)
+
+
+def head_logits_registered(t):
+    ent = HEAD_LOGITS.get(t.data_ptr())
+    return ent is not None and ent[0]() is not None and ent[1] == tuple(t.shape) and t.is_contiguous() \
+        and t.dtype == torch.float32
 
 
 class _LastLayer(nn.Module):
@@ -54,11 +66,15 @@ class DINOHead(nn.Module):
     def bf16_copies(self):
         return list(zip(self._bf16_srcs(), self._bf16)) if self._bf16 is not None else []
 
+    # freshness rule: see VisionTransformer (encoder.py) -- every forward re-casts unless the fused optimizer vouched
     def bf16_mark_fresh(self):
         self._bf16_ver = tuple(p._version for p in self._bf16_srcs())
 
+    def bf16_invalidate(self):
+        self._bf16_ver = None
+
     def bf16_is_fresh(self):
-        return self._bf16_ver == tuple(p._version for p in self._bf16_srcs())
+        return self._bf16_ver is not None and self._bf16_ver == tuple(p._version for p in self._bf16_srcs())
 
     def _bf16_weights(self):
         params = self._bf16_srcs()
@@ -67,11 +83,10 @@ class DINOHead(nn.Module):
             self._bf16 = [torch.empty(s.shape, dtype=torch.bfloat16, device=s.device) for s in srcs]
             self._wn = torch.empty(self.last_layer.weight_v.shape, dtype=torch.bfloat16, device=srcs[0].device)
             self._bf16_ver = None
-        ver = tuple(p._version for p in params)
-        if ver != self._bf16_ver:             # skipped while fresh (see VisionTransformer._bf16_weights)
+        if not self.bf16_is_fresh():
             table, n = self._cast.get(srcs, self._bf16, 2)
             ops.multi_tensor(ops.MT_CAST_BF16, table, n)
-            self._bf16_ver = ver
+        self._bf16_ver = None                                  # one-shot: consumed by this forward
         return self._bf16
 
     def forward(self, x):
@@ -107,6 +122,10 @@ class HeadFn(torch.autograd.Function):
             ctx.save_for_backward(xb, p1, a1, p2, a2, h3, yn, inv, wn, winv, wg, wv)
             ctx.wb = wb
             ctx.logits_ptr = logits.data_ptr()
+            for k in [k for k, (w, _) in HEAD_LOGITS.items() if w() is None]:        # forwards whose graph is gone
+                HEAD_LOGITS.pop(k, None)
+                DLOGITS_STASH.pop(k, None)
+            HEAD_LOGITS[ctx.logits_ptr] = (weakref.ref(ctx), (R2, K))
         return logits
 
     @staticmethod
@@ -118,9 +137,15 @@ class HeadFn(torch.autograd.Function):
         K, bott = wv.shape
         hid = p1.shape[1]
         b16 = dict(dtype=torch.bfloat16, device=dev)
-        dz = DLOGITS_STASH.pop(ctx.logits_ptr, None)
-        if dz is None or d_logits.stride() != (0, 0):
+        HEAD_LOGITS.pop(ctx.logits_ptr, None)
+        stash = DLOGITS_STASH.pop(ctx.logits_ptr, None)
+        if stash is None:
             dz = ops.cast_bf16(d_logits.contiguous().float())      # generic path: any upstream gradient
+        elif d_logits.data_ptr() == stash[1]:
+            dz = stash[0]                                          # fast path: autograd carried only the placeholder
+        else:
+            # the logits also fed something else: autograd summed that gradient with the (all-zero) placeholder
+            dz = ops.cast_bf16(d_logits.contiguous().float() + stash[0].float())
         # last layer
         dw = torch.zeros(K, bott, dtype=torch.float32, device=dev)
         ops.linear_wgrad(dz, yn, dw)

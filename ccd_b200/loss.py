@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import ops
-from .head import DLOGITS_STASH
+from .head import DLOGITS_STASH, head_logits_registered
 
 
 class DinoCEFn(torch.autograd.Function):
@@ -24,7 +24,8 @@ class DinoCEFn(torch.autograd.Function):
         # the centre is updated in place right after the forward (Dino_loss.py:104): backward needs the OLD centre
         ctx.save_for_backward(zs_c, zt_c, center.detach().clone().view(-1), stats)
         ctx.temps = (student_temp, teacher_temp)
-        ctx.zs_ptr = zs.data_ptr()
+        # the bf16 hand-off to HeadFn.backward is only valid when zs IS the tensor a ccd_b200 DINOHead produced
+        ctx.zs_ptr = zs.data_ptr() if head_logits_registered(zs) else None
         return loss.view(())
 
     @staticmethod
@@ -32,11 +33,13 @@ class DinoCEFn(torch.autograd.Function):
         zs, zt, center, stats = ctx.saved_tensors
         ts, tt = ctx.temps
         dz = ops.dino_ce_bwd(zs, zt, center, stats, g.contiguous().float().view(1), ts, tt)
+        if ctx.zs_ptr is None:
+            return dz.float(), None, None, None, None          # foreign logits: an ordinary dense gradient
         # fast path: hand the bf16 dlogits to HeadFn.backward (it consumes them as the GEMM A operand); autograd itself
         # only sees a zero-stride placeholder, so no fp32 [2R,K] gradient is ever materialised.
-        DLOGITS_STASH[ctx.zs_ptr] = dz
-        placeholder = torch.zeros(1, 1, dtype=zs.dtype, device=zs.device).expand(zs.shape)
-        return placeholder, None, None, None, None
+        placeholder = torch.zeros(1, 1, dtype=zs.dtype, device=zs.device)
+        DLOGITS_STASH[ctx.zs_ptr] = (dz, placeholder.data_ptr())
+        return placeholder.expand(zs.shape), None, None, None, None
 
 
 class SegCEFn(torch.autograd.Function):

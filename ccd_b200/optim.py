@@ -29,10 +29,11 @@ class AdamW(torch.optim.Optimizer):
 
     # ---- state_dict interchange with torch.optim.AdamW: 'step' is a tensor there, a python int here ----
     def state_dict(self):
+        # torch's Optimizer.state_dict() hands out the LIVE per-parameter dicts: build copies, never write into them
         sd = super().state_dict()
-        for st in sd["state"].values():
-            if "step" in st and not torch.is_tensor(st["step"]):
-                st["step"] = torch.tensor(float(st["step"]))
+        sd["state"] = {k: ({**st, "step": torch.tensor(float(st["step"]))}
+                           if "step" in st and not torch.is_tensor(st["step"]) else dict(st))
+                       for k, st in sd["state"].items()}
         return sd
 
     def load_state_dict(self, state_dict):
@@ -166,9 +167,9 @@ class AdamW(torch.optim.Optimizer):
             ops.fused_adamw(table, plan["grad_ptrs"], n, g["lr"], b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** step,
                             1.0 - b2 ** step, float(clip_grad) if want_norms else 0.0, float(ema_momentum))
         touched = [p for _, _, ps in todo for p in ps] + [t for _, t in ema_pairs]
-        # a module's bf16 copies stay valid if they were valid before and every parameter touched here was re-cast here
-        fresh = [m for m in mods if m.bf16_copies() and m.bf16_is_fresh()
-                 and all(id(p) in plan["recast"] for p, _ in m.bf16_copies() if id(p) in plan["updated"])]
+        # this pass vouches for a module's bf16 copies only if it rewrote EVERY one of them (parameter and copy in the same
+        # kernel); anything else is re-cast by the module's next forward (encoder.py: freshness rule)
+        fresh = [m for m in mods if m.bf16_copies() and all(id(p) in plan["recast"] for p, _ in m.bf16_copies())]
         if touched:
             torch.autograd.graph.increment_version(touched)       # raw-pointer in-place updates
         for m in fresh:

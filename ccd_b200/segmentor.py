@@ -127,6 +127,7 @@ def _bn_forward_group(items, training):
             else:
                 dist.all_reduce(sums[0])
         for (bn, z, ldz, M, C, y, ldy), sm in zip(items, sums):
+            # every rank holds the same number of rows: the reference's loader is built with drop_last=True (train.py:436-444)
             count = float(M) * world
             mom = 0.1 if bn.momentum is None else bn.momentum
             mean, rstd = ops.bn_finalize(sm, count, bn.eps, mom, bn.running_mean if bn.track_running_stats else None,
@@ -135,8 +136,9 @@ def _bn_forward_group(items, training):
                 bn.num_batches_tracked += 1
             out.append((mean, rstd, count))
     else:
+        # eval: running statistics are constants of the layer -> count = inf marks "no batch-statistic terms" for the backward
         for (bn, z, ldz, M, C, y, ldy) in items:
-            out.append((bn.running_mean.float(), torch.rsqrt(bn.running_var.float() + bn.eps), float(M)))
+            out.append((bn.running_mean.float(), torch.rsqrt(bn.running_var.float() + bn.eps), float("inf")))
     for (bn, z, ldz, M, C, y, ldy), (mean, rstd, _) in zip(items, out):
         ops.bn_apply_relu(z, ldz, mean, rstd, bn.weight.detach(), bn.bias.detach(), y, ldy, M, C)
     return out
@@ -152,7 +154,10 @@ def _bn_backward_group(items):
             for (bn, dy, lddy, z, ldz, mean, rstd, count, M, C) in items]
     # local sums = parameter gradients (dgamma, dbeta); DDP averages them across ranks
     pgrads = [(sm[it[9]:].clone(), sm[:it[9]].clone()) for sm, it in zip(sums, items)]
-    if _sync(items[0][0]):
+    # eval-mode forward (running statistics, count = inf): dz = dy * gamma * rstd under the ReLU mask -- no reduction terms
+    # (1/count = 0 zeroes them in bn_bwd_apply) and no SyncBN exchange
+    frozen = items[0][7] == float("inf")
+    if _sync(items[0][0]) and not frozen:
         if len(sums) > 1:
             flat = torch.cat(sums)
             dist.all_reduce(flat)

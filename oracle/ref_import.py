@@ -2,8 +2,9 @@
 in this container so the oracle restatement (oracle/ccd_oracle.py) can be pinned against it and golden
 vectors can be generated (tests/golden/make_golden.py).
 
-/root/reference does not exist on the GPU box: nothing under tests/ -m gpu, smoke() or bench.py may call
-this module.  Only third-party *imports* that are missing from this image are stubbed; no reference
+/root/reference does not exist on the GPU box; there the reference is the verbatim, hash-verified copy
+oracle/_ref made by oracle/build_ref.py (git-ignored, travels with the snapshot).  Users: tests/, bench.py's reference
+arms (--impl reference / stock-cuda) and nothing else; the product path never imports this module.  Only third-party *imports* that are missing from this image are stubbed; no reference
 arithmetic is replaced except skimage.measure.label, which is restated with scipy.ndimage.label
 (8-connectivity, raster-order labels -- the same labelling skimage's default connectivity produces;
 reference call site Dino/utils/DBSCAN.py:80).
@@ -18,7 +19,22 @@ import types
 import warnings
 from pathlib import Path
 
-REFERENCE_ROOT = os.environ.get("CCD_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    """CCD_REFERENCE_ROOT if set; else the reference checkout of this container; else the verbatim copy that
+    oracle/build_ref.py made of it (oracle/_ref, hash-checked against oracle/ref_manifest.json) -- the only form in which the
+    reference reaches the GPU box."""
+    env = os.environ.get("CCD_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/Dino"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:

@@ -22,14 +22,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ref_import  # noqa: E402
 from ccd_b200 import synthetic as S  # noqa: E402
 
-CASES = {
-    # name: (arch, E, batch, out_dim, student weight seed, teacher weight seed, std, norm_last_layer)
-    "cfg1_tiny_b4": ("vit_tiny", 192, 4, 65536, 1, 2, 0.05, False),
-    "small_b3": ("vit_small", 384, 3, 8192, 3, 4, 0.04, True),
-    "base_b2": ("vit_base", 512, 2, 4096, 5, 6, 0.03, False),
-}
-COL_STRIDE = 61          # logits columns kept: 0, 61, 122, ...
-GRAD_HEAD = 24           # leading elements of every gradient kept
+sys.path.insert(0, HERE)
+from cases import CASES, COL_STRIDE, COL_STRIDE_OF, EPOCH, GRAD_HEAD, SEG_KEEP  # noqa: E402
 
 
 def compact_from_onehot(z):
@@ -50,28 +44,32 @@ def run_case(ref, name, arch, E, B, K, sseed, tseed, std, norm_last):
     for p in teacher.parameters():
         p.requires_grad = False
     x, masks, metrics = S.make_batch(B, seed=1234)
-    loss_mod = ref.loss.DINOLoss(K, 2, 0.04, 0.04, 0, 10)
+    loss_mod = ref.loss.DINOLoss(K, 2, 0.04, 0.04, 0, 10 if EPOCH.get(name, 0) < 10 else 101)
     center0 = 0.01 * torch.randn(1, K, generator=torch.Generator().manual_seed(5))
     loss_mod.center.copy_(center0)
 
-    so = student(x, metrics, masks, 0, clusters=None)                                   # train.py:232
+    epoch = EPOCH.get(name, 0)
+    stride = COL_STRIDE_OF.get(name, COL_STRIDE)
+    so = student(x, metrics, masks, epoch, clusters=None)                               # train.py:232
     to = teacher(x, metrics, None, None, clusters=so["zero"], index=so["index"])        # train.py:233
     ag = F.affine_grid(metrics[:, :2, :], size=(B, 1, 32, 128))                         # train.py:234-236
     mi = (F.grid_sample(masks.unsqueeze(1), ag) > 0.1).float().squeeze()
     so["gt"] = [masks, mi]
-    loss = loss_mod(so, to, 0)                                                          # train.py:238
+    loss = loss_mod(so, to, epoch)                                                      # train.py:238
     loss.backward()
 
     out = {
         "loss": loss.item(), "mask_loss": loss_mod.last_losses["mask_loss"].item(),
         "dino_loss": loss_mod.last_losses["Dino_loss"].item(),
-        "student_logits": so["instances_view"].detach()[:, ::COL_STRIDE].numpy(),
-        "teacher_logits": to["instances_view"].detach()[:, ::COL_STRIDE].numpy(),
-        "seg_logits": so["mask"].detach().numpy().astype(np.float16),
+        "student_logits": so["instances_view"].detach()[:, ::stride].numpy(),
+        "teacher_logits": to["instances_view"].detach()[:, ::stride].numpy(),
+        "seg_logits": (so["mask"].detach() if name not in SEG_KEEP else
+                       torch.cat([so["mask"].detach()[:SEG_KEEP[name]], so["mask"].detach()[B:B + SEG_KEEP[name]]])
+                       ).numpy().astype(np.float16 if epoch < 30 else np.float32),
         "clusters_compact": compact_from_onehot(so["zero"]),
         "new_index": so["index"].numpy(),
         "gt_warped": mi.numpy().astype(np.uint8),
-        "center_after": loss_mod.center[:, ::COL_STRIDE].numpy(),
+        "center_after": loss_mod.center[:, ::stride].numpy(),
         "teacher_feature": to["feature"].detach()[:, ::7, :, ::3].numpy(),
     }
     names, norms, heads = [], [], []
@@ -114,9 +112,12 @@ def main():
     ref = ref_import.load_reference()
     ref_import.ensure_gloo_group()
     torch.manual_seed(0)
-    run_ccl(ref)
+    only = sys.argv[1:]
+    if not only:
+        run_ccl(ref)
     for name, cfg in CASES.items():
-        run_case(ref, name, *cfg)
+        if not only or name in only:
+            run_case(ref, name, *cfg)
 
 
 if __name__ == "__main__":

@@ -9,11 +9,9 @@ import ccd_oracle as O
 from ccd_b200 import synthetic as S
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = {
-    "cfg1_tiny_b4": ("vit_tiny", 192, 4, 65536, 1, 2, 0.05, False),
-    "small_b3": ("vit_small", 384, 3, 8192, 3, 4, 0.04, True),
-    "base_b2": ("vit_base", 512, 2, 4096, 5, 6, 0.03, False),
-}
+import sys
+sys.path.insert(0, GOLD)
+from cases import CASES, EPOCH, SEG_KEEP, col_stride  # noqa: E402
 
 
 def shapes(arch, E, K, student=True):
@@ -56,22 +54,32 @@ def test_pos_embed_is_linear_operator():
 @pytest.mark.parametrize("name", list(CASES))
 def test_oracle_step_matches_reference_golden(name):
     arch, E, B, K, sseed, tseed, std, norm_last = CASES[name]
+    epoch, cs = EPOCH.get(name, 0), col_stride(name)
     g = np.load(os.path.join(GOLD, name + ".npz"))
     ssd = S.fill_state_dict(shapes(arch, E, K, True), sseed, std)
     tsd = S.fill_state_dict(shapes(arch, E, K, False), tseed, std)
     sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in ssd.items()}
     x, masks, metrics = S.make_batch(B, seed=1234)
     center0 = 0.01 * torch.randn(1, K, generator=torch.Generator().manual_seed(5))
-    L, parts = O.pretrain_loss(sd, tsd, arch, x, metrics, masks, center0, 0, 0.04)
+    # epoch >= 30: the mask is a threshold of the segmentation logits -- compare the logits, then label the reference's
+    # (a last-bit difference on a pixel at the threshold would otherwise change the component structure)
+    own = None
+    if epoch >= 30:
+        own = torch.tensor(g["seg_logits"])
+        with torch.no_grad():
+            seg = O.student_forward(ssd, arch, x, metrics, masks, 0)["mask"]
+        assert (seg - own).abs().max() < 1e-4
+        assert ((seg[:, 1] > seg[:, 0]) != (own[:, 1] > own[:, 0])).float().mean() < 1e-4
+    L, parts = O.pretrain_loss(sd, tsd, arch, x, metrics, masks, center0, epoch, 0.04, self_mask_logits=own)
     L.backward()
     assert abs(L.item() - g["loss"]) < 2e-5 * abs(g["loss"])
     assert abs(parts["mask_loss"].item() - g["mask_loss"]) < 1e-5
     assert abs(parts["Dino_loss"].item() - g["dino_loss"]) < 2e-5 * g["dino_loss"]
-    assert np.abs(parts["student"]["instances_view"].detach().numpy()[:, ::61] - g["student_logits"]).max() < 1e-5
-    assert np.abs(parts["teacher"]["instances_view"].detach().numpy()[:, ::61] - g["teacher_logits"]).max() < 1e-5
+    assert np.abs(parts["student"]["instances_view"].detach().numpy()[:, ::cs] - g["student_logits"]).max() < 1e-5
+    assert np.abs(parts["teacher"]["instances_view"].detach().numpy()[:, ::cs] - g["teacher_logits"]).max() < 1e-5
     assert np.array_equal(parts["student"]["index"].numpy(), g["new_index"])
     assert np.array_equal(parts["gt"][B:].numpy().astype(np.uint8), g["gt_warped"])
-    assert np.abs(parts["center"].numpy()[:, ::61] - g["center_after"]).max() < 1e-7
+    assert np.abs(parts["center"].numpy()[:, ::cs] - g["center_after"]).max() < 1e-7
     dense = parts["student"]["zero"].numpy()
     assert np.array_equal((dense[:B] * np.arange(1, 27)[None, :, None, None]).sum(1).astype(np.uint8), g["clusters_compact"][:B])
     for n, norm, head in zip(g["grad_names"], g["grad_norms"], g["grad_heads"]):
