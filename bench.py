@@ -389,17 +389,6 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
     B = args.batch
-    # ---- BASELINE.md B1 sample, embedded like cpu_baseline: the reference's own train() + modules on this same GPU, before this
-    # arm allocates anything (N = 1 only; `--impl stock-cuda` under torch.distributed.run measures it at any N)
-    stock = None
-    if world == 1 and not finetune and not args.no_stock_baseline:
-        env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC")}
-        env.update(RANK="0", WORLD_SIZE="1", LOCAL_RANK=str(local), MASTER_ADDR="127.0.0.1")
-        stock = {"what": "reference train() + reference modules on CUDA (train.py:45-302 unmodified via oracle/run_ref_train.py), "
-                         f"{args.arch} batch {B}, out_dim {args.out_dim}, synthetic batches, 1 GPU", "unit": "images/s"}
-        for mode, ac, port in (("autocast_bf16", "bf16", 29711), ("fp32", "none", 29712)):
-            env["MASTER_PORT"] = str(port)
-            stock[mode] = stock_cuda_run(args.arch, B, args.out_dim, int(os.environ.get("CCD_STOCK_STEPS", "8")), 3, ac, timeout_s=600, env=env)
     if finetune:
         trainer = FinetuneStep(arch=args.arch, batch_per_gpu=B, drop_path_rate=0.1, device=dev, ddp=ddp)
         trainer.model.train()
@@ -463,6 +452,17 @@ def main():
         e2e = {"value": B * world * K / (t.item() / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": 4 * world}
 
+    # ---- BASELINE.md B1 sample, embedded like cpu_baseline: the reference's own train() + modules on this same GPU, AFTER this
+    # arm's timed regions (a second process; 180 GB of HBM hold both) (N = 1 only; `--impl stock-cuda` under torch.distributed.run measures it at any N)
+    stock = None
+    if world == 1 and not finetune and not args.no_stock_baseline:
+        env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC")}
+        env.update(RANK="0", WORLD_SIZE="1", LOCAL_RANK=str(local), MASTER_ADDR="127.0.0.1")
+        stock = {"what": "reference train() + reference modules on CUDA (train.py:45-302 unmodified via oracle/run_ref_train.py), "
+                         f"{args.arch} batch {B}, out_dim {args.out_dim}, synthetic batches, 1 GPU", "unit": "images/s"}
+        for mode, ac, port in (("autocast_bf16", "bf16", 29711), ("fp32", "none", 29712)):
+            env["MASTER_PORT"] = str(port)
+            stock[mode] = stock_cuda_run(args.arch, B, args.out_dim, int(os.environ.get("CCD_STOCK_STEPS", "8")), 3, ac, timeout_s=600, env=env)
     if rank != 0:
         if ddp:
             dist.destroy_process_group()

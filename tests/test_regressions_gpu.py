@@ -134,8 +134,15 @@ def test_seghead_eval_mode_backward_uses_running_statistics():
         u, v = u.double().flatten(), v.double().flatten()
         return (u @ v / (u.norm() * v.norm() + 1e-30)).item()
     assert ((out - want).norm() / want.norm()).item() < 2e-2
-    for u, v in zip(a, b):
-        assert cos(u.grad, v.grad) > 0.995
+    # same bar as the training-mode SegHead tests (bf16 activations through 8 layers, test_syncbn_2rank_gpu.py); applying the
+    # training-mode BatchNorm backward here instead drops these cosines to ~0.9 and below
+    cs = [cos(u.grad, v.grad) for u, v in zip(a, b)]
+    assert min(cs) > 0.985, cs
     gp, gr = dict(head.named_parameters()), dict(ref.named_parameters())
     for k in ("mlahead.head2.0.weight", "mlahead.head3.1.weight", "unpool1.0.weight", "unpool2.1.bias", "cls.weight"):
-        assert cos(gp[k].grad, gr[k].grad) > 0.99, k
+        assert cos(gp[k].grad, gr[k].grad) > 0.985, (k, cos(gp[k].grad, gr[k].grad))
+    # the training-mode formula on the same inputs is measurably different (so the test can tell the two apart)
+    head.train()
+    c = [t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True) for t in taps]
+    (head(c) * dl).sum().backward()
+    assert min(cos(u.grad, v.grad) for u, v in zip(c, b)) < min(cs) - 0.01
