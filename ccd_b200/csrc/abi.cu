@@ -1,2 +1,2 @@
-// ABI identification for include/ccd_b200.h
-extern "C" int ccd_abi_version(void) { return 1; }
+#include "ccd_common.cuh"
+extern "C" int ccd_abi_version(void) { return 2; }

@@ -152,6 +152,21 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store (shared -> global, bulk async-group completion) -- SASS: UTMASTG.  The shared tile is laid out exactly as a TMA load
+// of the same box would leave it (SWIZZLE_128B: 16-byte chunk c of row r at chunk position c ^ (r & 7)).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread's bulk groups have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// named barrier among `nthreads` threads of the CTA (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // tcgen05: TMEM alloc, UMMA, commit, TMEM load/store  -- SASS: UTCHMMA / LDTM / STTM
 // ---------------------------------------------------------------------------------------------------------
@@ -200,6 +215,20 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Same descriptor, `byte_off` further into the tile: only the 14-bit start-address field moves (shared memory < 256 KB, so the
+// sum never carries into the LBO field).  With a base descriptor computed once per kernel, every MMA of an unrolled loop costs
+// one uniform-register add instead of re-deriving shift / mask / or chains.
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t byte_off) {
+  return desc + (uint64_t)(byte_off >> 4);
+}
+// A CTA that allocates all 512 columns owns the whole tensor memory of its SM, so the allocation starts at column 0, lane 0.
+// Using the literal (checked once against what tcgen05.alloc wrote) makes every TMEM address a compile-time constant: the
+// value read back from shared memory lives in a vector register, and each tcgen05.mma fed from it costs two extra
+// R2UR.BROADCAST on the single issuing thread (cuobjdump -sass: 13-15 instructions per UTCHMMA before, 8-12 after).
+__device__ __forceinline__ uint32_t tmem_full_base(const uint32_t* slot) {
+  if (*slot != 0u) __trap();
+  return 0u;
 }
 // Instruction descriptor for kind::f16, BF16 x BF16 -> F32: c_format=1 [4,6) | a_format=1 [7,10) | b_format=1 [10,13) |
 // a_major [15] | b_major [16] (0 = K-major, 1 = MN-major) | N>>3 [17,23) | M>>4 [24,29).

@@ -112,8 +112,11 @@ __global__ void __launch_bounds__(256) mhsa_delta_kernel(const bf16* __restrict_
   }
 }
 
-// qkv-bias gradient = column sums of dqkv, produced by the pipelined kernel itself:
-//   query part  sum_q dQ[q, d]   and value part  sum_keys dV[key, d]   from the TMEM tiles as they are written out (below);
+// qkv-bias gradient = column sums of dqkv:
+//   query part  sum_q dQ[q, d]: produced by the pipelined kernel itself from the TMEM tiles as they are written out (below);
+//   value part  sum_keys dV[key, d] = sum_q (sum_keys P[q, key]) dO[q, d] = sum_q dO[q, d] (softmax rows sum to 1) = the column
+//               sums of d_o = (column sums of the proj-layer output gradient) . W_proj: a tiny vector-matrix product the caller
+//               does from the proj-bias gradient it already holds (ops.mhsa_bwd / ccd_vecmat_add_f32) -- no reduction here;
 //   key part    sum_keys dK[key, d] = sum_q (sum_keys dS[q, key]) Q[q, d] = 0 identically, because sum_keys dS[q, :] =
 //   scale (P . dP - delta[q]) = 0 (a key bias shifts every score of a row by the same amount): left untouched.
 // Per-CTA partial sums live in shared memory across all items of the persistent CTA and are flushed with one global atomic
@@ -135,6 +138,46 @@ __device__ __forceinline__ void store_tmem_row64_colsum(uint32_t taddr, bf16* ds
       o.z = pack_bf16x2(__uint_as_float(raw[8 * g + 4]), __uint_as_float(raw[8 * g + 5]));
       o.w = pack_bf16x2(__uint_as_float(raw[8 * g + 6]), __uint_as_float(raw[8 * g + 7]));
       *reinterpret_cast<uint4*>(dst + half * 32 + g * 8) = o;
+    }
+    if (colsum != nullptr) {
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const bool up = (lane & step) != 0;
+#pragma unroll
+        for (int k = 0; k < step; ++k) {
+          const float keep = up ? v[k + step] : v[k];
+          const float send = up ? v[k] : v[k + step];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+      }
+      atomicAdd(colsum + half * 32 + lane, v[0]);
+    }
+  }
+}
+
+// 64 fp32 TMEM columns of this thread's lane -> bf16 -> this thread's 128-byte row of a [128 x 64] shared tile in the
+// SWIZZLE_128B layout a TMA store expects (chunk c of row r at c ^ (r & 7)): conflict-free 16-byte stores, and the global
+// write becomes ONE bulk tensor store per tile instead of 8 x 128 scattered 16-byte stores per warp (each warp-level STG.128 of
+// the thread-per-row form touches 32 different 128-byte lines: the LSU serialises them, ~2400 cycles per tile measured).
+// colsum != NULL: also the column sums over the warp's 32 rows (value-halving butterfly, see store_tmem_row64_colsum).
+__device__ __forceinline__ void stage_tmem_row64(uint32_t taddr, uint32_t srow, int r, float* colsum, int lane) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t raw[32];
+    tmem_ld_32x32(taddr + half * 32, raw);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t a = pack_bf16x2(__uint_as_float(raw[8 * g + 0]), __uint_as_float(raw[8 * g + 1]));
+      const uint32_t b = pack_bf16x2(__uint_as_float(raw[8 * g + 2]), __uint_as_float(raw[8 * g + 3]));
+      const uint32_t c = pack_bf16x2(__uint_as_float(raw[8 * g + 4]), __uint_as_float(raw[8 * g + 5]));
+      const uint32_t d = pack_bf16x2(__uint_as_float(raw[8 * g + 6]), __uint_as_float(raw[8 * g + 7]));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)(((half * 4 + g) ^ (r & 7)) * 16)), "r"(a),
+                   "r"(b), "r"(c), "r"(d)
+                   : "memory");
     }
     if (colsum != nullptr) {
       float v[32];
@@ -350,23 +393,31 @@ mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #define CCD_ATT_TRACE 0
 #endif
 #if CCD_ATT_TRACE
+// Diagnostic build only (tools/att_trace.py).  CTA 0 records (event, item, sub-tile, clock) per role into SHARED memory -- one
+// LDS + two STS per record, ~50 cycles; the first version took a global atomicAdd per record (~1000 cycles each, on the single
+// issuing thread: the traced kernel ran 2.2x slower than the product and its proportions could not be trusted) -- and copies
+// the records to the global buffer when the kernel ends.  4 roles x ATT_TRACE_CAP records x 8 bytes after the product's layout.
+constexpr int ATT_TRACE_CAP = 640;
+constexpr int ATT_TRACE_BYTES = 4 * ATT_TRACE_CAP * 8 + 16;
 __device__ long long* g_att_trace_buf = nullptr;
 __device__ unsigned int g_att_trace_n = 0;
 __device__ unsigned int g_att_trace_cap = 0;
-__device__ __forceinline__ void att_trace(int role, int ev, int item, int sub) {
-  if (blockIdx.x != 0 || g_att_trace_buf == nullptr) return;
-  const unsigned int i = atomicAdd(&g_att_trace_n, 1u);
-  if (i < g_att_trace_cap) {
-    long long* r = g_att_trace_buf + 4 * (size_t)i;
-    r[0] = ((long long)role << 32) | (unsigned int)ev;
-    r[1] = item;
-    r[2] = sub;
-    r[3] = clock64();
+__device__ __forceinline__ void att_trace_at(uint8_t* base, int role, int ev, int item, int sub) {
+  if (blockIdx.x != 0) return;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(base) + role;
+  const uint32_t i = *cnt;
+  if (i < (uint32_t)ATT_TRACE_CAP) {
+    uint2* r = reinterpret_cast<uint2*>(base + 16) + role * ATT_TRACE_CAP + i;
+    *r = make_uint2((uint32_t)ev | ((uint32_t)sub << 8) | ((uint32_t)item << 16), (uint32_t)clock64());
+    *cnt = i + 1;
   }
 }
-#define ATT_TRACE(role, ev, item, sub) att_trace(role, ev, item, sub)
+#define ATT_TRACE(role, ev, item, sub) att_trace_at(att_trace_base, role, ev, item, sub)
+#define ATT_TRACE_L0(role, ev, item, sub) do { if ((threadIdx.x & 31) == 0) att_trace_at(att_trace_base, role, ev, item, sub); } while (0)
 #else
+constexpr int ATT_TRACE_BYTES = 0;
 #define ATT_TRACE(role, ev, item, sub) ((void)0)
+#define ATT_TRACE_L0(role, ev, item, sub) ((void)0)
 #endif
 // events: 1 wait begin / 2 wait end on bar_done (producer) ; 10/11 bar_qk+bar_vdo, 12/13 bar_pd, 14/15 bar_epi, 16 S/dP issued,
 // 17 dV/dK(/dQ) issued (issuer) ; 20/21 bar_free, 22/23 bar_s, 24 math + P/dS written, 25/26 bar_acc, 27 dK/dV/dQ stored (softmax)
@@ -402,20 +453,21 @@ __device__ __forceinline__ float4 lds128_b(uint32_t saddr) {
 
 __global__ void __launch_bounds__(ATB_THREADS, 1)
 mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                          const MhsaBwdParams p, int n_items) {
+                          const __grid_constant__ CUtensorMap tmDQKV, const MhsaBwdParams p, int n_items) {
   using L = MhsaBwd2Smem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* bar_qk = bars;           // Q, K of the item landed                       (1 completion / item)
-  uint64_t* bar_vdo = bars + 1;      // V, dO landed
+  uint64_t* bar_qk = bars;           // rows 0..127 of Q, K, V, dO + the lse / delta vectors landed   (1 completion / item)
+  uint64_t* bar_vdo = bars + 1;      // rows 128..255 of Q, K, V, dO landed
   uint64_t* bar_done = bars + 2;     // every MMA of the item retired: smem reusable   (1 / item)
   uint64_t* bar_s = bars + 3;        // [2] S^T_s, dP^T_s ready in TMEM stage          (4 / item each)
   uint64_t* bar_pd = bars + 5;       // [2] P^T (TMEM) and dS^T (smem) of sub-tile written, 128 arrivals (4 / item each)
   uint64_t* bar_free = bars + 7;     // [4] dS^T sub-block no longer read by an MMA    (2 / item each)
   uint64_t* bar_acc = bars + 11;     // dK_j, dV_j (and, for j = 1, dQ) complete       (2 / item)
   uint64_t* bar_epi = bars + 12;     // dK_j / dV_j (+dQ) read out of TMEM, 256 arrivals (2 / item)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* bar_stg = bars + 13;     // [2] warpgroup g's staged output tiles have been read by their TMA stores (2 / item each)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -431,11 +483,18 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     for (int i = 0; i < 4; ++i) mbar_init(&bar_free[i], 1);
     mbar_init(bar_acc, 1);
     mbar_init(bar_epi, 256);
+    mbar_init(&bar_stg[0], 1);
+    mbar_init(&bar_stg[1], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQKV);
   }
   float* csum = reinterpret_cast<float*>(smem + L::OFF_CSUM);
+#if CCD_ATT_TRACE
+  uint8_t* att_trace_base = smem + L::SMEM_BYTES - 1024;       // behind the product layout (the launch adds ATT_TRACE_BYTES)
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(att_trace_base)[threadIdx.x] = 0u;
+#endif
   pdl_launch_dependents();
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) csum[i] = 0.f;
   if (warp == 1) {
@@ -445,7 +504,7 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_full_base(tmem_slot);
   const uint32_t tDK = tmem_base + 256, tDV = tmem_base + 320, tDQ = tmem_base + 384;
   pdl_wait();                                      // delta / lse vectors and dO of the preceding kernels are complete and visible
 
@@ -459,19 +518,21 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         ATT_TRACE(0, 1, it, 0);
         mbar_wait(bar_done, (it & 1) ^ 1);            // previous item's MMAs no longer read Q/K/V/dO (passes for it = 0)
         ATT_TRACE(0, 2, it, 0);
+        // first halves (rows 0..127 of Q, K, V, dO) + the two vectors: everything the first two sub-tiles need
         mbar_arrive_expect_tx(bar_qk, 2 * L::TILE + 2048);
         // -lse2 and -delta*scale of the item's 256 queries (pre-formed by mhsa_delta_kernel), double buffered per item
         bulk_load_1d(smem + L::OFF_LSE + (it & 1) * 1024, p.nlse + (size_t)w * ATB_N, 1024, bar_qk);
         bulk_load_1d(smem + L::OFF_DELTA + (it & 1) * 1024, p.delta + (size_t)w * ATB_N, 1024, bar_qk);
-        for (int b = 0; b < 2; ++b) {
-          tma_load_2d(smem + L::OFF_K + b * 16384, &tmQKV, bar_qk, p.E + h * ATB_D, row0 + b * 128);
-          tma_load_2d(smem + L::OFF_Q + b * 16384, &tmQKV, bar_qk, h * ATB_D, row0 + b * 128);
-        }
+        tma_load_2d(smem + L::OFF_K, &tmQKV, bar_qk, p.E + h * ATB_D, row0);
+        tma_load_2d(smem + L::OFF_Q, &tmQKV, bar_qk, h * ATB_D, row0);
+        tma_load_2d(smem + L::OFF_V, &tmQKV, bar_qk, 2 * p.E + h * ATB_D, row0);
+        tma_load_2d(smem + L::OFF_DO, &tmDO, bar_qk, h * ATB_D, row0);
+        // second halves (rows 128..255): first needed by sub-tile 2, i.e. after the first softmax-gradient phase
         mbar_arrive_expect_tx(bar_vdo, 2 * L::TILE);
-        for (int b = 0; b < 2; ++b) {
-          tma_load_2d(smem + L::OFF_V + b * 16384, &tmQKV, bar_vdo, 2 * p.E + h * ATB_D, row0 + b * 128);
-          tma_load_2d(smem + L::OFF_DO + b * 16384, &tmDO, bar_vdo, h * ATB_D, row0 + b * 128);
-        }
+        tma_load_2d(smem + L::OFF_Q + 16384, &tmQKV, bar_vdo, h * ATB_D, row0 + 128);
+        tma_load_2d(smem + L::OFF_DO + 16384, &tmDO, bar_vdo, h * ATB_D, row0 + 128);
+        tma_load_2d(smem + L::OFF_K + 16384, &tmQKV, bar_vdo, p.E + h * ATB_D, row0 + 128);
+        tma_load_2d(smem + L::OFF_V + 16384, &tmQKV, bar_vdo, 2 * p.E + h * ATB_D, row0 + 128);
       }
     }
   } else if (warp == 1) {
@@ -482,25 +543,32 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       const uint32_t id_s = umma_idesc_bf16(128, 64, 0, 0);    // S^T / dP^T sub-tile: K-major x K-major, N = 64 queries
       const uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dV / dK: A K-major (TMEM or smem), B MN-major
       const uint32_t id_nn = umma_idesc_bf16(128, 64, 1, 1);   // dQ: A MN-major, B MN-major
+      // base descriptors, one per (tile, layout); every MMA below advances one of them by a constant (umma_desc_advance): the
+      // issuing thread is the critical resource of this kernel -- N = 64 MMAs execute in 32 cycles, so re-deriving two
+      // descriptors per MMA (plus the TMEM-address waterfall, see tmem_full_base) made the ISSUE, not the tensor pipe, the limit
+      const uint64_t dK_k = umma_smem_desc_sw128(aK, 16, 1024), dQ_k = umma_smem_desc_sw128(aQ, 16, 1024),      // K-major
+                     dV_k = umma_smem_desc_sw128(aV, 16, 1024), dDO_k = umma_smem_desc_sw128(aDO, 16, 1024),
+                     dDS_k = umma_smem_desc_sw128(aDS, 16, 1024);
+      const uint64_t dDO_m = umma_smem_desc_sw128(aDO, 8192, 1024), dQ_m = umma_smem_desc_sw128(aQ, 8192, 1024),  // MN-major
+                     dK_m = umma_smem_desc_sw128(aK, 8192, 1024), dDS_m = umma_smem_desc_sw128(aDS, 16384, 1024);
       // sub-tile s: key tile j = s >> 2, queries [64 qs, 64 qs + 64) with qs = s & 3 (row offset qs * 8192 B in Q / dO)
       auto issue_s = [&](int s) {
         const int j = s >> 2, qs = s & 3;
         const uint32_t tS = tmem_base + (s & 1) * 128;
+        const uint64_t a0 = umma_desc_advance(dK_k, j * 16384), b0 = umma_desc_advance(dQ_k, qs * 8192);
+        const uint64_t a1 = umma_desc_advance(dV_k, j * 16384), b1 = umma_desc_advance(dDO_k, qs * 8192);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_ss(tS, umma_smem_desc_sw128(aK + j * 16384 + ks * 32, 16, 1024),
-                  umma_smem_desc_sw128(aQ + qs * 8192 + ks * 32, 16, 1024), id_s, ks > 0 ? 1u : 0u);
+          umma_ss(tS, umma_desc_advance(a0, ks * 32), umma_desc_advance(b0, ks * 32), id_s, ks > 0 ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_ss(tS + 64, umma_smem_desc_sw128(aV + j * 16384 + ks * 32, 16, 1024),
-                  umma_smem_desc_sw128(aDO + qs * 8192 + ks * 32, 16, 1024), id_s, ks > 0 ? 1u : 0u);
+          umma_ss(tS + 64, umma_desc_advance(a1, ks * 32), umma_desc_advance(b1, ks * 32), id_s, ks > 0 ? 1u : 0u);
         umma_commit(&bar_s[s & 1]);
       };
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         ATT_TRACE(1, 10, it, 0);
-        mbar_wait(bar_qk, it & 1);
-        mbar_wait(bar_vdo, it & 1);
+        mbar_wait(bar_qk, it & 1);                    // first halves: enough for sub-tiles 0 and 1
         ATT_TRACE(1, 11, it, 0);
         tc_fence_after();
         issue_s(0);
@@ -519,30 +587,36 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           }
           tc_fence_after();
           const uint32_t tP = tmem_base + g * 128;    // bf16 P^T over the first 32 columns of the stage
-          const uint32_t aDSq = aDS + qs * 16384;
+          const uint64_t bDO = umma_desc_advance(dDO_m, qs * 8192), bQ = umma_desc_advance(dQ_m, qs * 8192),
+                         aDSq = umma_desc_advance(dDS_k, qs * 16384);
+          const uint32_t acc0 = qs > 0 ? 1u : 0u;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {            // contraction over the 64 queries of the sub-tile
             // dV_j += P^T dO_s        (dO sub-tile read MN-major: 16 query rows = 2048 B)
-            umma_ts(tDV, tP + ks * 8, umma_smem_desc_sw128(aDO + qs * 8192 + ks * 2048, 8192, 1024), id_kn,
-                    (qs > 0 || ks > 0) ? 1u : 0u);
+            umma_ts(tDV, tP + ks * 8, umma_desc_advance(bDO, ks * 2048), id_kn, ks > 0 ? 1u : acc0);
             // dK_j += dS^T Q_s
-            umma_ss(tDK, umma_smem_desc_sw128(aDSq + ks * 32, 16, 1024),
-                    umma_smem_desc_sw128(aQ + qs * 8192 + ks * 2048, 8192, 1024), id_kn, (qs > 0 || ks > 0) ? 1u : 0u);
+            umma_ss(tDK, umma_desc_advance(aDSq, ks * 32), umma_desc_advance(bQ, ks * 2048), id_kn, ks > 0 ? 1u : acc0);
           }
           if (qs & 1) {
             // dQ_I += dS_I K_j over the 128 keys, I = qs >> 1: A = sub-blocks (qs-1, qs) read MN-major (64-query chunks
             // 16 KB apart, 16 key rows = 2048 B)
             const int I = qs >> 1;
+            const uint64_t aDSI = umma_desc_advance(dDS_m, I * 32768), bK = umma_desc_advance(dK_m, j * 16384);
+            const uint32_t accq = j > 0 ? 1u : 0u;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              umma_ss(tDQ + I * 64, umma_smem_desc_sw128(aDS + I * 32768 + ks * 2048, 16384, 1024),
-                      umma_smem_desc_sw128(aK + j * 16384 + ks * 2048, 8192, 1024), id_nn, (j > 0 || ks > 0) ? 1u : 0u);
+              umma_ss(tDQ + I * 64, umma_desc_advance(aDSI, ks * 2048), umma_desc_advance(bK, ks * 2048), id_nn,
+                      ks > 0 ? 1u : accq);
             umma_commit(&bar_free[qs - 1]);
             umma_commit(&bar_free[qs]);
           }
           if (qs == 3) umma_commit(bar_acc);
           if (s == 7) umma_commit(bar_done);
           ATT_TRACE(1, 17, it, s);
+          if (s == 0) {                               // sub-tile 2 is the first to read rows 128..255 (Q / dO), then K / V of tile 1
+            mbar_wait(bar_vdo, it & 1);
+            tc_fence_after();
+          }
           if (s + 2 < 8) issue_s(s + 2);              // overwrites stage g: after the dV MMAs above (in-order) and after
         }                                             // warpgroup g finished reading it (bar_pd)
       }
@@ -558,6 +632,7 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     const uint32_t sDS = smem_u32(smem + L::OFF_DS);
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
     int it = 0;
+    int n_epi = 0;                                    // epilogues this warpgroup has issued (two per item)
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int s_idx = w / p.H, h = w - s_idx * p.H;
       const int row0 = s_idx * ATB_N;
@@ -570,6 +645,8 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         const bool tr = (lane == 0 && q4 == ((2 + 4 * g) & 3));      // lane 0 of the warpgroup's first warp
         if (tr) ATT_TRACE(2 + g, 20, it, s);
         mbar_wait(&bar_free[qs], j ^ 1);              // the dQ / dK MMAs that read this dS^T sub-block have retired
+        // ... and so have the TMA stores of the output tiles this warpgroup staged in the dS^T sub-blocks at its last epilogue
+        if (qs < 2 && n_epi > 0) mbar_wait(&bar_stg[g], (n_epi - 1) & 1);
         if (tr) { ATT_TRACE(2 + g, 21, it, s); ATT_TRACE(2 + g, 22, it, s); }
         mbar_wait(&bar_s[g], (s >> 1) & 1);
         if (tr) ATT_TRACE(2 + g, 23, it, s);
@@ -628,16 +705,26 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           mbar_wait(bar_acc, j);
           if (tr) ATT_TRACE(2 + g, 26, it, s);
           tc_fence_after();
-          bf16* drow = p.dqkv + ((size_t)row0 + j * 128 + r) * (3 * p.E) + h * ATB_D;
+          // Every MMA of key tile j has retired, so the four dS^T sub-blocks are idle: sub-block 2 + g takes dK_j (g = 0) /
+          // dV_j (g = 1), and after the second key tile sub-block g takes dQ rows [128 g, 128 g + 128).  The accumulators are
+          // handed back (bar_epi) as soon as they are in shared memory; ONE thread per warpgroup then issues the bulk tensor
+          // stores.  Both sub-blocks are next written by THIS warpgroup (qs = g and qs = 2 + g are its sub-tiles): bar_stg[g].
           const bool want_bias = p.dbias != nullptr;
-          if (g == 0) store_tmem_row64(tDK + lane_sel, drow + p.E);
-          else        store_tmem_row64_colsum(tDV + lane_sel, drow + 2 * p.E, want_bias ? csum + 512 + h * 64 : nullptr, lane);
-          if (j == 1) {
-            bf16* qrow = p.dqkv + ((size_t)row0 + g * 128 + r) * (3 * p.E) + h * ATB_D;
-            store_tmem_row64_colsum(tDQ + g * 64 + lane_sel, qrow, want_bias ? csum + h * 64 : nullptr, lane);
-          }
+          const uint32_t stage_kv = sDS + (2 + g) * 16384, stage_q = sDS + g * 16384;
+          stage_tmem_row64((g == 0 ? tDK : tDV) + lane_sel, stage_kv + r * 128, r, nullptr, lane);
+          if (j == 1) stage_tmem_row64(tDQ + g * 64 + lane_sel, stage_q + r * 128, r, want_bias ? csum + h * 64 : nullptr, lane);
           tc_fence_before();
           mbar_arrive(bar_epi);
+          fence_proxy_async_smem();
+          named_bar_sync(1 + g, 128);
+          if (q4 == ((2 + 4 * g) & 3) && lane == 0) {
+            tma_store_2d(&tmDQKV, smem + L::OFF_DS + (2 + g) * 16384, (g == 0 ? p.E : 2 * p.E) + h * ATB_D, row0 + j * 128);
+            if (j == 1) tma_store_2d(&tmDQKV, smem + L::OFF_DS + g * 16384, h * ATB_D, row0 + g * 128);
+            tma_store_commit();
+            tma_store_wait_read();
+            mbar_arrive(&bar_stg[g]);
+          }
+          ++n_epi;
           if (tr) ATT_TRACE(2 + g, 27, it, s);
         }
       }
@@ -646,14 +733,34 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (p.dbias != nullptr) {          // flush this CTA's column sums: q part at [0, E), v part at [2E, 3E)
-    for (int i = threadIdx.x; i < 2 * p.H * 64; i += blockDim.x) {
-      const int part = i / (p.H * 64), c = i - part * (p.H * 64);
-      const float v = csum[part * 512 + c];
-      if (v != 0.f) atomicAdd(p.dbias + part * 2 * p.E + c, v);
+  if (p.dbias != nullptr) {          // flush this CTA's column sums of dQ: the q part [0, E) of the qkv-bias gradient
+    for (int i = threadIdx.x; i < p.H * 64; i += blockDim.x) {
+      const float v = csum[i];
+      if (v != 0.f) atomicAdd(p.dbias + i, v);
     }
   }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+#if CCD_ATT_TRACE
+  if (blockIdx.x == 0 && g_att_trace_buf != nullptr) {          // after the __syncthreads above: every role's records are visible
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(att_trace_base);
+    for (int role = 0; role < 4; ++role) {
+      const uint32_t n = cnt[role];
+      uint32_t off = 0;
+      for (int r2 = 0; r2 < role; ++r2) off += cnt[r2];
+      const uint2* src = reinterpret_cast<const uint2*>(att_trace_base + 16) + role * ATT_TRACE_CAP;
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        if (off + i >= g_att_trace_cap) break;
+        long long* dst = g_att_trace_buf + 4 * (size_t)(off + i);
+        const uint2 v = src[i];
+        dst[0] = ((long long)role << 32) | (v.x & 0xFFu);
+        dst[1] = v.x >> 16;
+        dst[2] = (v.x >> 8) & 0xFFu;
+        dst[3] = v.y;
+      }
+    }
+    if (threadIdx.x == 0) g_att_trace_n = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+  }
+#endif
 }
 
 }  // namespace ccd
@@ -663,13 +770,17 @@ using namespace ccd;
 // C ABI -- see include/ccd_b200.h
 static int g_mhsa_bwd_variant = 1;   // 1 = pipelined persistent kernel (default), 0 = one CTA per (sequence, head)
 
+extern "C" int ccd_colsum_bf16(const void* x, float* out, int rows, int cols, void* stream);
+extern "C" int ccd_vecmat_add_f32(const float* v, const float* W, float* out, int rows, int cols, void* stream);
+
 extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, float* delta_ws, void* dqkv,
-                            float* dbias_qkv, int S, int H, void* stream_) {
+                            float* dbias_qkv, const float* dproj_bias, const float* w_proj, int S, int H, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!qkv || !o || !d_o || !lse2 || !delta_ws || !dqkv || S <= 0 || H <= 0 || H > 8) return CCD_ERR_ARG;
   if (dbias_qkv != nullptr && g_mhsa_bwd_variant != 1) return CCD_ERR_UNSUPPORTED;   // fused bias gradient: pipelined kernel only
   const int E = H * ATB_D;
-  CUtensorMap tmQKV, tmDO;
+  CUtensorMap tmQKV, tmDO, tmDQKV;
+  if (!get_tmap_bf16_2d(&tmDQKV, dqkv, (uint64_t)S * ATB_N, (uint64_t)3 * E, (uint64_t)3 * E, 128, 64)) return CCD_ERR_TMAP;
   if (!get_tmap_bf16_2d(&tmQKV, qkv, (uint64_t)S * ATB_N, (uint64_t)3 * E, (uint64_t)3 * E, 128, 64)) return CCD_ERR_TMAP;
   if (!get_tmap_bf16_2d(&tmDO, d_o, (uint64_t)S * ATB_N, (uint64_t)E, (uint64_t)E, 128, 64)) return CCD_ERR_TMAP;
   MhsaBwdParams p;
@@ -699,7 +810,7 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
     static int num_sms = 148;
     if (!attr2_set) {
       CCD_CUDA_CHECK(cudaFuncSetAttribute(mhsa_bwd_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          MhsaBwd2Smem::SMEM_BYTES));
+                                          MhsaBwd2Smem::SMEM_BYTES + ATT_TRACE_BYTES));
       int dev = 0;
       CCD_CUDA_CHECK(cudaGetDevice(&dev));
       CCD_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -707,7 +818,11 @@ extern "C" int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, con
     }
     const int n_items = S * H;
     CCD_CUDA_CHECK(launch_pdl(mhsa_bwd_pipelined_kernel, dim3(n_items < num_sms ? n_items : num_sms), dim3(ATB_THREADS),
-                              (size_t)MhsaBwd2Smem::SMEM_BYTES, stream, tmQKV, tmDO, p, n_items));
+                              (size_t)(MhsaBwd2Smem::SMEM_BYTES + ATT_TRACE_BYTES), stream, tmQKV, tmDO, tmDQKV, p, n_items));
+    if (dbias_qkv != nullptr) {       // v part of the qkv-bias gradient = column sums of d_o (see the comment above the kernel)
+      if (dproj_bias != nullptr && w_proj != nullptr) return ccd_vecmat_add_f32(dproj_bias, w_proj, dbias_qkv + 2 * E, E, E, stream_);
+      return ccd_colsum_bf16(d_o, dbias_qkv + 2 * E, S * ATB_N, E, stream_);
+    }
     return CCD_OK;
   }
   dim3 grid(H, S);

@@ -279,7 +279,7 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_full_base(tmem_slot);      // all 512 columns: literal 0 (see ccd_common.cuh)
   pdl_wait();                                      // qkv of the preceding GEMM is complete and visible
 
   if (warp == 0) {
@@ -310,18 +310,22 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
       // the MUFU never idles while a tile waits for its MMAs):   S0(0) | S1(i)  O0(i)  S0(i+1)  O1(i) | ...
       // S_t(i+1) overwrites the TMEM columns of P_t(i) / O_t(i): it is issued after O_t(i) (MMAs retire in issue order)
       // and after the epilogue of tile t has read O_t(i) out (tmem_free[t]).
-      auto issue_s = [&](int t, uint32_t buf) {
+      // one base descriptor per layout; each MMA advances it by a constant (the 16 N = 64 MMAs of O = P V execute in 32 cycles
+      // each: deriving descriptors per MMA on the single issuing thread cost more than the MMAs themselves)
+      const uint64_t d_k = umma_smem_desc_sw128(smem_u32(smem), 16, 1024);          // K-major tiles (Q, K)
+      const uint64_t d_v = umma_smem_desc_sw128(smem_u32(smem), 8192, 1024);        // V read MN-major
+      auto issue_s = [&](int t, uint32_t buf_off) {
+        const uint64_t a = umma_desc_advance(d_k, buf_off + t * 16384), b = umma_desc_advance(d_k, buf_off + 32768);
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k)
-          umma_ss(tmem_base + t * 256, umma_smem_desc_sw128(buf + t * 16384 + k * 32, 16, 1024),
-                  umma_smem_desc_sw128(buf + 32768 + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_ss(tmem_base + t * 256, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * 32), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&s_full[t]);
       };
-      auto issue_o = [&](int t, uint32_t buf) {
+      auto issue_o = [&](int t, uint32_t buf_off) {
+        const uint64_t b = umma_desc_advance(d_v, buf_off + 65536);
 #pragma unroll
         for (int k = 0; k < ATT_N / 16; ++k)
-          umma_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8,
-                  umma_smem_desc_sw128(buf + 65536 + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+          umma_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8, umma_desc_advance(b, k * 2048), idesc_o, k > 0 ? 1u : 0u);
         umma_commit(&o_full[t]);
       };
       // (A polling issuer that serves the two tiles as independent chains was measured 6-12 % SLOWER than this fixed
@@ -330,12 +334,12 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
       if (blockIdx.x < n_items) {
         mbar_wait(&full_qk[0], 0);
         tc_fence_after();
-        issue_s(0, smem_u32(smem));
+        issue_s(0, 0u);
       }
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int b = it & 1;
         const uint32_t kph = (it >> 1) & 1, ph = it & 1;
-        const uint32_t buf = smem_u32(smem + b * ATT2_BUF);
+        const uint32_t buf = (uint32_t)(b * ATT2_BUF);          // byte offset of this item's Q/K/V buffer
         mbar_wait(&tmem_free[1], ph ^ 1);         // previous item's O_1 has been read out of TMEM
         tc_fence_after();
         issue_s(1, buf);
@@ -348,7 +352,7 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
           mbar_wait(&full_qk[it1 & 1], (it1 >> 1) & 1);
           mbar_wait(&tmem_free[0], (it1 & 1) ^ 1);
           tc_fence_after();
-          issue_s(0, smem_u32(smem + (it1 & 1) * ATT2_BUF));
+          issue_s(0, (uint32_t)((it1 & 1) * ATT2_BUF));
         }
         mbar_wait(&p_full[1], ph);
         tc_fence_after();

@@ -452,6 +452,26 @@ extern "C" int ccd_colsum_bf16(const void* x, float* out, int rows, int cols, vo
   return CCD_OK;
 }
 
+// out[c] += sum_r v[r] * W[r, c]: one thread per column, rows split over blockIdx.y (coalesced over c; a few hundred KB at most)
+__global__ void __launch_bounds__(128) vecmat_add_f32_kernel(const float* __restrict__ v, const float* __restrict__ W,
+                                                             float* __restrict__ out, int rows, int cols, int rpb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rpb, r1 = min(rows, r0 + rpb);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc = fmaf(v[r], W[(size_t)r * cols + c], acc);
+  atomicAdd(out + c, acc);
+}
+
+extern "C" int ccd_vecmat_add_f32(const float* v, const float* W, float* out, int rows, int cols, void* stream) {
+  if (!v || !W || !out || rows <= 0 || cols <= 0) return CCD_ERR_ARG;
+  const int rpb = 32;
+  dim3 grid((cols + 127) / 128, (rows + rpb - 1) / rpb);
+  vecmat_add_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(v, W, out, rows, cols, rpb);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
 extern "C" int ccd_colsum_f32(const float* x, float* out, int rows, int cols, void* stream) {
   if (!x || !out || rows <= 0 || cols <= 0 || (cols & 3)) return CCD_ERR_ARG;
   const int rpb = 64;

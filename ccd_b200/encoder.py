@@ -301,7 +301,9 @@ class VitFn(torch.autograd.Function):
             ops.linear_wgrad(dx2b, o, grads[pi + 4])                # proj.bias grad came from the LN2 backward above
             d_o = torch.empty(T, E, **b16)
             ops.linear_dgrad(dx2b, wproj, ops.EPI_BF16, d_o)
-            dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, n, H, dbias=grads[pi + 3])              # qkv.bias grad in the same kernels
+            # qkv.bias grad: q part inside the kernel, v part = (proj.bias grad) @ W_proj (column sums of d_o), k part = 0
+            dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, n, H, dbias=grads[pi + 3], dproj_bias=grads[pi + 5],
+                                w_proj=params[pi + 4].detach())
             ops.linear_wgrad(dqkv, xn, grads[pi + 2])
             dxn = torch.empty(T, E, **b16)
             ops.linear_dgrad(dqkv, wqkv, ops.EPI_BF16, dxn)

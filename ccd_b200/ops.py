@@ -18,7 +18,7 @@ _CTYPE = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_lo
           "unsigned long long": ctypes.c_ulonglong}
 _FN = {}
 LAUNCHES = [0]     # number of kernels launched through the C ABI (bench.py reports it)
-KERNELS_PER_CALL = {"ccd_dino_ce_fwd": 2, "ccd_seg_ce_fwd": 2, "ccd_char_plan": 3, "ccd_mhsa_bwd": 2}
+KERNELS_PER_CALL = {"ccd_dino_ce_fwd": 2, "ccd_seg_ce_fwd": 2, "ccd_char_plan": 3, "ccd_mhsa_bwd": 3}
 # bench.py roofline instrumentation: when a dict, every call of a listed entry point is bracketed by CUDA events on
 # the launching stream:  PROFILE = {"names": {"ccd_gemm_bf16", ...}, "events": []}
 PROFILE = None
@@ -153,13 +153,17 @@ def mhsa_fwd(qkv, S, H, want_lse=True, variant=None):
 _MHSA_BWD_VARIANT = [1]
 
 
-def mhsa_bwd(qkv, o, d_o, lse, S, H, dbias=None):
-    """dqkv of the fused attention; `dbias` (optional, zero-filled f32 [3E]) accumulates the qkv-bias gradient in the
-    same kernels (pipelined variant) or through a column-sum pass over dqkv (first variant)."""
+def mhsa_bwd(qkv, o, d_o, lse, S, H, dbias=None, dproj_bias=None, w_proj=None):
+    """dqkv of the fused attention; `dbias` (optional, zero-filled f32 [3E]) accumulates the qkv-bias gradient: the q part inside
+    the pipelined kernel, the v part (= column sums of d_o) as `dproj_bias @ w_proj` when the caller holds the proj-bias
+    gradient (f32 [E]) and the proj weight (f32 [E,E]) -- otherwise by a column-sum pass over d_o; first variant: a column-sum
+    pass over dqkv."""
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((2,) + tuple(lse.shape), dtype=torch.float32, device=lse.device)     # workspace [2,S,H,256]
     fused = dbias is not None and _MHSA_BWD_VARIANT[0] == 1
+    vm = fused and dproj_bias is not None and w_proj is not None
     _call("ccd_mhsa_bwd", _p(qkv), _p(o), _p(_chk(d_o, torch.bfloat16)), _p(lse), _p(delta), _p(dqkv), _p(dbias) if fused else None,
+          _p(_chk(dproj_bias, torch.float32)) if vm else None, _p(_chk(w_proj, torch.float32)) if vm else None,
           S, H, _s(), work=(10.0 * 256 * 256 * 64 * S * H, (S, H)))
     if dbias is not None and not fused:
         colsum_bf16(dqkv, dbias)
@@ -202,6 +206,12 @@ def layernorm_bwd(x, gamma, dy, resid, dgamma, dbeta, want_f32=True, want_bf16=T
 def colsum_bf16(x, out_zeroed):
     _call("ccd_colsum_bf16", _p(_chk(x, torch.bfloat16)), _p(out_zeroed), x.shape[0], x.shape[1], _s())
     return out_zeroed
+
+
+def vecmat_add(v, W, out):
+    """out[c] += sum_r v[r] W[r, c]  (f32)."""
+    _call("ccd_vecmat_add_f32", _p(_chk(v, torch.float32)), _p(_chk(W, torch.float32)), _p(out), W.shape[0], W.shape[1], _s())
+    return out
 
 
 def colsum_f32(x, out_zeroed):

@@ -47,11 +47,18 @@ int ccd_mhsa_fwd(const void* qkv, void* out, float* lse2, int S, int H, int vari
 /* Fused MHSA backward: -> dqkv bf16 [S*256, 3*H*64]; delta_ws = f32 [2,S,H,256] workspace (rowsum(O*dO) and the negated
  * log-sum-exp in the form the main kernel consumes, written by a small pre-pass).  Replaces autograd of vision_transformer.py:85-89. */
 int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, float* delta_ws, void* dqkv,
-                 float* dbias_qkv, int S, int H, void* stream);
-/* dbias_qkv (optional, f32 [3*H*64], caller zero-fills): gradient of Attention.qkv.bias = column sums of dqkv, accumulated by
- * the backward kernel itself from the dQ and dV tiles as they leave TMEM (per-CTA partial sums in shared memory, one
- * global atomic per (head, column) and CTA); the key part is identically zero (a key bias shifts all scores of a row
- * equally) and is left untouched.  Pipelined variant only (CCD_ERR_UNSUPPORTED otherwise). */
+                 float* dbias_qkv, const float* dproj_bias, const float* w_proj, int S, int H, void* stream);
+/* dbias_qkv (optional, f32 [3*H*64], caller zero-fills): gradient of Attention.qkv.bias = column sums of dqkv.
+ *   q part: accumulated by the backward kernel itself from the dQ tiles as they leave TMEM (per-CTA partial sums in shared
+ *           memory, one global atomic per (head, column) and CTA);
+ *   k part: identically zero (a key bias shifts all scores of a row equally), left untouched;
+ *   v part: sum_keys dV = sum_q dO (softmax rows sum to 1) = column sums of d_o.  When the caller passes the gradient of
+ *           Attention.proj.bias (dproj_bias f32 [E] = column sums of the proj output gradient) and the proj weight (w_proj f32
+ *           [E,E], nn.Linear layout) this is the vector-matrix product dproj_bias . w_proj (d_o = dY . W_proj); with NULLs the
+ *           entry point column-sums d_o itself.
+ * Pipelined variant only (CCD_ERR_UNSUPPORTED otherwise). */
+/* out[c] += sum_r v[r] * W[r, c]   (f32, W row-major [rows, cols]) */
+int ccd_vecmat_add_f32(const float* v, const float* W, float* out, int rows, int cols, void* stream);
 /* A/B switch (debug): 1 = pipelined persistent backward kernel (default), 0 = first version (one CTA per (sequence, head)) */
 int ccd_set_mhsa_bwd_variant(int value);
 

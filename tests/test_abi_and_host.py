@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 47
     for s in syms:
         assert hasattr(L, s), s
-    assert L.ccd_abi_version() == 1
+    assert L.ccd_abi_version() == 2
 
 
 def test_argument_validation_without_gpu():

@@ -175,6 +175,28 @@ def test_mhsa_bwd(ops, S, H, variant):
     assert want[E:2 * E].abs().max().item() < 1e-6 * scale          # the key part vanishes analytically
 
 
+def test_mhsa_bwd_bias_gradient_from_proj_bias_gradient(ops):
+    """The v part of the qkv-bias gradient as the encoder obtains it: d_o = dY W_proj, so colsum(d_o) = colsum(dY) W_proj
+    (ccd_vecmat_add_f32 inside ccd_mhsa_bwd) -- against autograd of the attention with a v-bias."""
+    S, H = 3, 6
+    E = H * 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = _bf(torch.randn(S * 256, 3 * E, device="cuda", generator=g))
+    dY = torch.randn(S * 256, E, device="cuda", generator=g)
+    W = torch.randn(E, E, device="cuda", generator=g) * 0.05
+    d_o = _bf(dY @ W)
+    o, lse = ops.mhsa_fwd(qkv, S, H, True, 0)
+    dbias = torch.zeros(3 * E, device="cuda")
+    dqkv = ops.mhsa_bwd(qkv, o, d_o, lse, S, H, dbias=dbias, dproj_bias=dY.sum(0).contiguous(), w_proj=W.contiguous())
+    torch.cuda.synchronize()
+    want = dqkv.double().sum(0)
+    scale = want.abs().max().item()
+    assert (dbias.double() - want).abs().max().item() < 2e-2 * scale
+    out = torch.zeros(E, device="cuda")
+    ops.vecmat_add(dY.sum(0).contiguous(), W.contiguous(), out)
+    assert _rel(out, dY.double().sum(0) @ W.double()) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------------------
 # row-wise kernels
 # ---------------------------------------------------------------------------------------------------------

@@ -49,9 +49,11 @@ n = ctypes.c_uint(0)
 L.ccd_debug_att_trace_count(ctypes.byref(n))
 L.ccd_debug_att_trace(None, 0)
 rec = buf[: min(n.value, CAP)].cpu().tolist()
+# the per-role record buffers (shared memory) hold a different number of items per role: keep the items every role covered
+items = min(max(r[1] for r in rec if (r[0] >> 32) == role) for role in {r[0] >> 32 for r in rec})
+rec = [r for r in rec if r[1] < items]
 rec.sort(key=lambda r: r[3])
 t0 = rec[0][3]
-items = max(r[1] for r in rec) + 1
 per_role = collections.defaultdict(lambda: collections.defaultdict(int))
 open_wait = {}
 last = {}
