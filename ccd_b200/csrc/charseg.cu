@@ -365,6 +365,118 @@ __global__ void new_index_kernel(const int* __restrict__ cnt, unsigned char* __r
   if (i < n_view * SLOTS) out[i] = (i % SLOTS) < cnt[i / SLOTS] ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Text-mask generation: 2-means over the grey levels of one crop + border-majority polarity rule
+// (clusterpixels, mask_create/generate_mask.py:13-29 = Dino/utils/kmeans.py:8-24).
+//
+// The reference runs scipy.cluster.vq.kmeans(k = 2) -- Lloyd iterations from 20 random initialisations, best distortion
+// kept -- and then assigns every pixel to its nearest centroid (vq).  In one dimension the partition Lloyd converges to is a
+// threshold on the grey level, and the minimum-distortion one is found EXACTLY from the 256-bin histogram: maximise
+// s0^2/n0 + s1^2/n1 over the 255 thresholds (prefix sums).  One CTA per image:
+//   histogram (shared-memory atomics) -> block-wide prefix sums -> arg-max threshold -> centroids c0 < c1 -> code = grey > (c0+c1)/2
+//   -> sums of the code over the first / last column and row -> flip when >= 3 of them exceed half (the rule that makes the
+//   text the 1-cluster whichever centroid came first) -> mask f32 {0,1} [H,W], directly consumable by ccd_ccl_label mode 0.
+// Centroid order is canonical (dark = 0, bright = 1); the reference's order depends on its random initialisation, which only
+// shows when exactly two of the four border sums exceed half (its answer then depends on the seed).  Constant images give an
+// all-zero mask (scipy drops the empty cluster).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kmeans_mask_kernel(const uint8_t* __restrict__ grey, float* __restrict__ mask, int H, int W) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long pre_n[256], pre_s[256];      // inclusive prefix counts / grey-level sums
+  __shared__ double best_j[8];
+  __shared__ int best_t[8];
+  __shared__ unsigned int border[4];                          // code sums: first col, last col, first row, last row
+  __shared__ float s_mid;
+  __shared__ int s_flip, s_const;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int npx = H * W;
+  const uint8_t* img = grey + (size_t)blockIdx.x * npx;
+  float* out = mask + (size_t)blockIdx.x * npx;
+  hist[tid] = 0u;
+  if (tid < 4) border[tid] = 0u;
+  __syncthreads();
+  for (int i = tid; i < npx; i += 256) atomicAdd(&hist[img[i]], 1u);
+  __syncthreads();
+  // inclusive scan of (count, count * level) over the 256 bins: warp shuffles, then the 8 warp totals
+  unsigned long long n = hist[tid], sm = (unsigned long long)hist[tid] * (unsigned long long)tid;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long n2 = __shfl_up_sync(0xffffffffu, n, o), s2 = __shfl_up_sync(0xffffffffu, sm, o);
+    if (lane >= o) { n += n2; sm += s2; }
+  }
+  pre_n[tid] = n;
+  pre_s[tid] = sm;
+  __syncthreads();
+  unsigned long long off_n = 0, off_s = 0;
+  for (int w = 0; w < wrp; ++w) { off_n += pre_n[w * 32 + 31]; off_s += pre_s[w * 32 + 31]; }
+  __syncthreads();
+  n += off_n;
+  sm += off_s;
+  pre_n[tid] = n;
+  pre_s[tid] = sm;
+  __syncthreads();
+  const unsigned long long N = pre_n[255], S = pre_s[255];
+  // threshold t = tid: class 0 = levels <= t.  J(t) = s0^2/n0 + s1^2/n1 in double (s <= 255 * 2^20: squares are exact)
+  double j = -1.0;
+  if (tid < 255 && n > 0 && n < N) {
+    const double s0 = (double)sm, s1 = (double)(S - sm);
+    j = s0 * s0 / (double)n + s1 * s1 / (double)(N - n);
+  }
+  int t = tid;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {                         // arg-max, ties -> smallest threshold
+    const double j2 = __shfl_xor_sync(0xffffffffu, j, o);
+    const int t2 = __shfl_xor_sync(0xffffffffu, t, o);
+    if (j2 > j || (j2 == j && t2 < t)) { j = j2; t = t2; }
+  }
+  if (lane == 0) { best_j[wrp] = j; best_t[wrp] = t; }
+  __syncthreads();
+  if (tid == 0) {
+    double bj = best_j[0];
+    int bt = best_t[0];
+    for (int w = 1; w < 8; ++w)
+      if (best_j[w] > bj || (best_j[w] == bj && best_t[w] < bt)) { bj = best_j[w]; bt = best_t[w]; }
+    if (bj < 0.0) {                                           // a single grey level: one cluster, every code 0
+      s_const = 1;
+      s_mid = 256.0f;
+    } else {
+      const double c0 = (double)pre_s[bt] / (double)pre_n[bt];
+      const double c1 = (double)(S - pre_s[bt]) / (double)(N - pre_n[bt]);
+      s_const = 0;
+      s_mid = (float)(0.5 * (c0 + c1));                       // |v - c1| < |v - c0|  <=>  v > (c0 + c1) / 2  (ties -> code 0, as vq's arg-min)
+    }
+  }
+  __syncthreads();
+  const float mid = s_mid;
+  // border sums of the code (generate_mask.py:21-24)
+  unsigned int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  for (int y = tid; y < H; y += 256) {
+    b0 += (float)img[y * W] > mid;
+    b1 += (float)img[y * W + W - 1] > mid;
+  }
+  for (int x = tid; x < W; x += 256) {
+    b2 += (float)img[x] > mid;
+    b3 += (float)img[(H - 1) * W + x] > mid;
+  }
+  if (b0) atomicAdd(&border[0], b0);
+  if (b1) atomicAdd(&border[1], b1);
+  if (b2) atomicAdd(&border[2], b2);
+  if (b3) atomicAdd(&border[3], b3);
+  __syncthreads();
+  if (tid == 0) {
+    const int num = (int)(border[2] > (unsigned)(W / 2)) + (int)(border[3] > (unsigned)(W / 2)) + (int)(border[0] > (unsigned)(H / 2)) +
+                    (int)(border[1] > (unsigned)(H / 2));
+    s_flip = (num >= 3) ? 1 : 0;
+  }
+  __syncthreads();
+  const bool flip = s_flip != 0;
+  for (int i = tid; i < npx; i += 256) {
+    const bool code = (float)img[i] > mid;
+    out[i] = (code != flip) ? 1.0f : 0.0f;
+  }
+}
+
 }  // namespace ccd
 
 using namespace ccd;
@@ -378,6 +490,13 @@ extern "C" int ccd_ccl_label(const float* src, int mode, void* bits_u32, void* c
     attr_set = true;
   }
   ccl_label_kernel<<<n_img, 256, smem, (cudaStream_t)stream>>>(src, mode, (unsigned*)bits_u32, (unsigned char*)compact_u8, n_comp);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_kmeans_mask(const void* grey_u8, float* mask, int n_img, int H, int W, void* stream) {
+  if (!grey_u8 || !mask || n_img <= 0 || H < 2 || W < 2 || (long long)H * W > (1 << 20)) return CCD_ERR_ARG;
+  kmeans_mask_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)grey_u8, mask, H, W);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }

@@ -9,7 +9,7 @@
 //     dP^T = V_j dO_i^T           [keys x queries]   cols [128,256)
 //     P^T  = exp2(S^T c - lse2[q]);  dS^T = P^T (dP^T - delta[q]) * scale     (thread = key row)
 //     dV_j += P^T  dO_i           cols [320,384)     (dO read MN-major)
-//     dK_j += dS^T Q_i            cols [256,320)     (Q  read MN-major)
+//     dK_j += dS^T Q_i            cols [256,320)     (Q  read MN-major; pipelined kernel: dS^T as a TMEM A operand)
 //     dQ_i += dS   K_j            cols [384,512)     (dS^T tile read MN-major as A, K read MN-major)
 // P^T / dS^T go through shared memory as bf16 in the 128B-swizzled layout that is simultaneously a K-major A tile
 // (for dV, dK) and an MN-major A tile (for dQ).
@@ -547,8 +547,7 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       // issuing thread is the critical resource of this kernel -- N = 64 MMAs execute in 32 cycles, so re-deriving two
       // descriptors per MMA (plus the TMEM-address waterfall, see tmem_full_base) made the ISSUE, not the tensor pipe, the limit
       const uint64_t dK_k = umma_smem_desc_sw128(aK, 16, 1024), dQ_k = umma_smem_desc_sw128(aQ, 16, 1024),      // K-major
-                     dV_k = umma_smem_desc_sw128(aV, 16, 1024), dDO_k = umma_smem_desc_sw128(aDO, 16, 1024),
-                     dDS_k = umma_smem_desc_sw128(aDS, 16, 1024);
+                     dV_k = umma_smem_desc_sw128(aV, 16, 1024), dDO_k = umma_smem_desc_sw128(aDO, 16, 1024);
       const uint64_t dDO_m = umma_smem_desc_sw128(aDO, 8192, 1024), dQ_m = umma_smem_desc_sw128(aQ, 8192, 1024),  // MN-major
                      dK_m = umma_smem_desc_sw128(aK, 8192, 1024), dDS_m = umma_smem_desc_sw128(aDS, 16384, 1024);
       // sub-tile s: key tile j = s >> 2, queries [64 qs, 64 qs + 64) with qs = s & 3 (row offset qs * 8192 B in Q / dO)
@@ -587,15 +586,14 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           }
           tc_fence_after();
           const uint32_t tP = tmem_base + g * 128;    // bf16 P^T over the first 32 columns of the stage
-          const uint64_t bDO = umma_desc_advance(dDO_m, qs * 8192), bQ = umma_desc_advance(dQ_m, qs * 8192),
-                         aDSq = umma_desc_advance(dDS_k, qs * 16384);
+          const uint64_t bDO = umma_desc_advance(dDO_m, qs * 8192), bQ = umma_desc_advance(dQ_m, qs * 8192);
           const uint32_t acc0 = qs > 0 ? 1u : 0u;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {            // contraction over the 64 queries of the sub-tile
             // dV_j += P^T dO_s        (dO sub-tile read MN-major: 16 query rows = 2048 B)
             umma_ts(tDV, tP + ks * 8, umma_desc_advance(bDO, ks * 2048), id_kn, ks > 0 ? 1u : acc0);
-            // dK_j += dS^T Q_s
-            umma_ss(tDK, umma_desc_advance(aDSq, ks * 32), umma_desc_advance(bQ, ks * 2048), id_kn, ks > 0 ? 1u : acc0);
+            // dK_j += dS^T Q_s        (dS^T from TMEM, bf16 pairs over columns [64,96) of the stage)
+            umma_ts(tDK, tP + 64 + ks * 8, umma_desc_advance(bQ, ks * 2048), id_kn, ks > 0 ? 1u : acc0);
           }
           if (qs & 1) {
             // dQ_I += dS_I K_j over the 128 keys, I = qs >> 1: A = sub-blocks (qs-1, qs) read MN-major (64-query chunks
@@ -688,6 +686,10 @@ mhsa_bwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           // P^T -> TMEM (bf16 pairs: 32 queries = 16 columns); the S^T columns it lands on were read in an earlier half
           // or just above (half 0 writes cols [0,16), read range of half 1 is [32,64))
           tmem_st_32x16(tS + half * 16, pp);
+          // dS^T -> TMEM as well (over dP^T columns already consumed: half 0 writes cols [64,80), half 1 reads [96,128)): the
+          // A operand of dK_j += dS^T Q (TS form) -- one 4 KB shared-memory operand read less per MMA; the shared-memory copy
+          // below remains for dQ, which reads the tile MN-major
+          tmem_st_32x16(tS + 64 + half * 16, dd);
           // dS^T -> shared memory: row = key r, 16-byte chunk (8 queries) index ^ (r & 7)
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4)

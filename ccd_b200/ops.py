@@ -414,6 +414,14 @@ def ccl_label(src, mode, n_img, want_compact=False):
     return bits, compact, ncomp
 
 
+def kmeans_mask(grey_u8):
+    """Text masks from grey crops (clusterpixels, mask_create/generate_mask.py:13-29): grey u8 [n,H,W] -> f32 {0,1} [n,H,W]."""
+    n, H, W = grey_u8.shape
+    out = torch.empty(n, H, W, dtype=torch.float32, device=grey_u8.device)
+    _call("ccd_kmeans_mask", _p(_chk(grey_u8, torch.uint8)), _p(out), n, H, W, _s())
+    return out
+
+
 def warp_bits(bits, theta):
     out = torch.empty_like(bits)
     _call("ccd_warp_bits", _p(bits), _p(_chk(theta, torch.float32)), _p(out), bits.shape[0], _s())

@@ -119,6 +119,10 @@ int ccd_seg_ce_bwd(const float* logits, const float* gt, const float* gscale_dev
  * mode 0: src = f32 masks [n,32,128]; mode 1: src = f32 seg logits [*,2,32,128] (foreground = logit1 > logit0).
  * bits u32 [n,32,128] (bit s = slot s) and/or compact u8 [n,32,128] (slot+1, 0 = background); n_comp int[n]. */
 int ccd_ccl_label(const float* src, int mode, void* bits_u32, void* compact_u8, int* n_comp, int n_img, void* stream);
+/* Text-mask generation (clusterpixels, mask_create/generate_mask.py:13-29): exact 2-means over the grey levels of each image
+ * (histogram + threshold scan) + the border-majority polarity flip.  grey u8 [n,H,W] -> mask f32 {0,1} [n,H,W] (text = 1), the
+ * form ccd_ccl_label mode 0 consumes.  H*W <= 2^20. */
+int ccd_kmeans_mask(const void* grey_u8, float* mask, int n_img, int H, int W, void* stream);
 /* affine_grid + bilinear grid_sample(zeros, align_corners=False) + (> 0.1): dino_vision.py:72-77, train.py:234-236 */
 int ccd_warp_bits(const void* src_bits, const float* theta, void* dst_bits, int n_img, void* stream);
 int ccd_warp_mask(const float* src, const float* theta, float* dst, int n_img, void* stream);

@@ -530,3 +530,39 @@ def test_gelu_epilogue_accuracy(ops):
     with open("gpurun_out/gelu_accuracy.json", "w") as f:
         json.dump(rec, f)
     assert err.max().item() < 1.5e-3 and derr.max().item() < 3e-3, rec
+
+
+# ---------------------------------------------------------------------------------------------------------
+# text-mask generation (first slice)
+# ---------------------------------------------------------------------------------------------------------
+def test_kmeans_mask_bit_exact_vs_oracle_and_reference_golden(ops):
+    """ccd_kmeans_mask against the numpy oracle (bit-exact: integer histogram + the same float64 objective) on the golden crops,
+    odd sizes, constant and two-level images; against the reference's own masks (tests/golden/kmeans_masks.npz) with the
+    oracle's criteria; and end to end into the component labelling."""
+    import os
+    import mask_oracle as MO
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmeans_masks.npz"))
+    imgs = z["images"]
+    got = ops.kmeans_mask(torch.from_numpy(imgs).cuda()).cpu().numpy().astype(np.uint8)
+    for i, im in enumerate(imgs):
+        assert np.array_equal(got[i], MO.cluster_pixels(im)), i
+    exact = sum(np.array_equal(g, w) for g, w in zip(got, z["masks"]))
+    assert exact >= 0.85 * len(imgs)
+    assert min((g == w).mean() for g, w in zip(got, z["masks"])) >= 0.985
+    # other sizes + degenerate images
+    for h, w, seed in ((48, 160, 3), (17, 33, 4), (64, 256, 5)):
+        ims = MO.synthetic_text_crops(5, h=h, w=w, seed=seed)
+        ims[0] = 93                                            # constant -> all zero
+        ims[1] = 200
+        ims[1, 2:h - 2, 5:9] = 15                              # two levels, dark text
+        out = ops.kmeans_mask(torch.from_numpy(ims).cuda()).cpu().numpy().astype(np.uint8)
+        for i in range(len(ims)):
+            assert np.array_equal(out[i], MO.cluster_pixels(ims[i])), (h, w, i)
+        assert out[0].sum() == 0 and out[1].sum() == (h - 4) * 4
+    # the masks feed the component labelling directly (same result as labelling the oracle's masks)
+    import ccd_oracle as O
+    m = ops.kmeans_mask(torch.from_numpy(imgs[:8]).cuda())
+    bits, compact, ncomp = ops.ccl_label(m, 0, 8, want_compact=True)
+    for i in range(8):
+        _, want = O.label_cluster(MO.cluster_pixels(imgs[i]).astype(np.float32))
+        assert np.array_equal(compact[i].cpu().numpy(), want), i
