@@ -463,6 +463,28 @@ __global__ void __launch_bounds__(128) vecmat_add_f32_kernel(const float* __rest
   atomicAdd(out + c, acc);
 }
 
+// C[M,N] = op(A) B in fp32 for the SMALL constant operators of the path (the 256 x 256 bicubic pos-embed resample):
+// op(A) = A [M,K] or A^T with A stored [K,M]; B [K,N]; one thread per output element, coalesced over n.
+__global__ void __launch_bounds__(128) smallmm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                                          int M, int N, int K, int trans_a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  if (!trans_a) {
+    for (int k = 0; k < K; ++k) acc = fmaf(A[(size_t)m * K + k], B[(size_t)k * N + n], acc);
+  } else {
+    for (int k = 0; k < K; ++k) acc = fmaf(A[(size_t)k * M + m], B[(size_t)k * N + n], acc);
+  }
+  C[(size_t)m * N + n] = acc;
+}
+
+extern "C" int ccd_smallmm_f32(const float* A, const float* B, float* C, int M, int N, int K, int trans_a, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || M > 65535) return CCD_ERR_ARG;
+  smallmm_f32_kernel<<<dim3((N + 127) / 128, M), 128, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, trans_a ? 1 : 0);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
 extern "C" int ccd_vecmat_add_f32(const float* v, const float* W, float* out, int rows, int cols, void* stream) {
   if (!v || !W || !out || rows <= 0 || cols <= 0) return CCD_ERR_ARG;
   const int rpb = 32;

@@ -110,7 +110,10 @@ class VisionTransformer(nn.Module):
             elif isinstance(m, nn.LayerNorm):
                 nn.init.constant_(m.bias, 0)
                 nn.init.constant_(m.weight, 1.0)
-        self.register_buffer("_pos_w", pos_resample_matrix(), persistent=False)
+        # constant of the architecture, NOT a registered buffer: DistributedDataParallel re-broadcasts every buffer from rank 0
+        # at each forward (256 KB here, on the critical path of the step)
+        self._pos_w_host = pos_resample_matrix()
+        self._pos_w_dev = {}
         self._cast = ops.ChunkTable()
         self._bf16 = None
         self._bf16_ver = None
@@ -170,6 +173,12 @@ class VisionTransformer(nn.Module):
         wp[:, :48] = self.patch_embed.proj.weight.detach().reshape(E, 48)
         return wp, self._bf16
 
+    def pos_w(self, device):
+        w = self._pos_w_dev.get(device)
+        if w is None:
+            w = self._pos_w_dev[device] = self._pos_w_host.to(device).contiguous()
+        return w
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("ccd_b200.VisionTransformer runs on CUDA (sm_100a) only; there is no CPU path")
@@ -203,7 +212,7 @@ class VitFn(torch.autograd.Function):
         b16 = dict(dtype=torch.bfloat16, device=dev)
         pos_embed, _, patch_b = params[0], params[1], params[2]
         cols = ops.patch_im2col(x_img)
-        pos_eff = torch.matmul(mod._pos_w, pos_embed.detach()[0])               # [256,E]: constant operator, host glue
+        pos_eff = ops.smallmm(mod.pos_w(dev), pos_embed.detach()[0].contiguous())  # [256,E] = W . pos_embed, fp32
         x = torch.empty(T, E, **f32)
         ops.gemm(cols, wp, T, E, 64, 0, 0, ops.EPI_POS, patch_b.detach(), x, None, pos_eff)
         saved = []
@@ -319,7 +328,7 @@ class VitFn(torch.autograd.Function):
         grads[1].copy_(d_wpatch[:, :48].reshape(grads[1].shape))
         dpos_eff = torch.zeros(GRID_TOKENS * E, dtype=torch.float32, device=dev)
         ops.colsum_f32(dx.view(n, GRID_TOKENS * E), dpos_eff)
-        grads[0].copy_(torch.matmul(mod._pos_w.t(), dpos_eff.view(GRID_TOKENS, E)).view(grads[0].shape))
+        grads[0].copy_(ops.smallmm(mod.pos_w(dev), dpos_eff.view(GRID_TOKENS, E), trans_a=True).view(grads[0].shape))
         return (None, None, None, None, None, *grads)
 
 

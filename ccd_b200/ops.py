@@ -208,6 +208,15 @@ def colsum_bf16(x, out_zeroed):
     return out_zeroed
 
 
+def smallmm(A, B, trans_a=False):
+    """C = op(A) @ B in f32 (small constant operators: the pos-embed resample matrix)."""
+    K, N = B.shape
+    M = A.shape[1] if trans_a else A.shape[0]
+    C = torch.empty(M, N, dtype=torch.float32, device=B.device)
+    _call("ccd_smallmm_f32", _p(_chk(A, torch.float32)), _p(_chk(B, torch.float32)), _p(C), M, N, K, 1 if trans_a else 0, _s())
+    return C
+
+
 def vecmat_add(v, W, out):
     """out[c] += sum_r v[r] W[r, c]  (f32)."""
     _call("ccd_vecmat_add_f32", _p(_chk(v, torch.float32)), _p(_chk(W, torch.float32)), _p(out), W.shape[0], W.shape[1], _s())

@@ -42,10 +42,18 @@ class PretrainStep:
                 self.student_module = student
             # train.py:106 uses find_unused_parameters=True (cls_token and segmentation.conv_mla.* never get gradients);
             # static_graph=True gives the same semantics without re-walking the autograd graph every iteration
+            # broadcast_buffers: train.py keeps DDP's default (rank 0's BatchNorm running statistics are re-broadcast at every
+            # forward); under SyncBatchNorm every rank already holds identical running statistics, so the broadcast -- one more
+            # NCCL kernel at the head of every step -- changes nothing and is switched off here (CCD_DDP_BROADCAST_BUFFERS=1 restores it)
             student = nn.parallel.DistributedDataParallel(student, device_ids=[self.device.index],
                                                           find_unused_parameters=True,
+                                                          broadcast_buffers=os.environ.get("CCD_DDP_BROADCAST_BUFFERS", "0") == "1",
                                                           gradient_as_bucket_view=os.environ.get("CCD_DDP_BUCKET_VIEW", "1") == "1",
                                                           static_graph=os.environ.get("CCD_DDP_STATIC", "1") == "1")
+            if os.environ.get("CCD_DDP_BF16_HOOK", "0") == "1":
+                # optional: gradients travel as bf16 (halves the 176.9 MiB all-reduce); off by default -- the reference reduces fp32
+                from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+                student.register_comm_hook(None, default_hooks.bf16_compress_hook)
         self.student, self.teacher = student, teacher
         self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
         self._loss_event = torch.cuda.Event()

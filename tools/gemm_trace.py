@@ -31,11 +31,10 @@ L = lib.load(build_if_missing=False)
 if not hasattr(L, "ccd_debug_gemm_trace"):
     raise SystemExit("this library was built without -DCCD_GEMM_TRACE=1 (see the docstring)")
 L.ccd_debug_gemm_trace.argtypes = [ctypes.c_void_p, ctypes.c_uint]
-L.ccd_debug_gemm_trace_count.argtypes = [ctypes.POINTER(ctypes.c_uint)]
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(0)
-CAP = 1 << 16
-buf = torch.zeros(CAP, 4, dtype=torch.int64, device=dev)
+CAP, ROLES = 4096, 11                    # csrc/gemm_umma.cu: GEMM_TRACE_CAP records per role region + 11 counters at the end
+buf = torch.zeros(ROLES * CAP + ROLES, dtype=torch.int64, device=dev)
 
 
 def rnd(*shape, scale=1.0):
@@ -63,14 +62,23 @@ for name in (sys.argv[1:] or ["fc1_fwd_gelu_nosave", "fc2_dgrad_dgelu", "qkv_fwd
     run = lambda: ops.gemm(A, B, M, N, K, amn, bmn, epi, bias, out0, out1, aux, 0, splits)
     run()
     torch.cuda.synchronize()
+    buf.zero_()
     assert L.ccd_debug_gemm_trace(buf.data_ptr(), CAP) == 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record()
     torch.cuda.synchronize()
-    n = ctypes.c_uint(0)
-    L.ccd_debug_gemm_trace_count(ctypes.byref(n))
     L.ccd_debug_gemm_trace(None, 0)
-    rec = buf[: min(n.value, CAP)].cpu().tolist()
+    host = buf.cpu().numpy().view("uint64")
+    rec = []
+    for role in ROLE:
+        cnt = int(host[ROLES * CAP + role])
+        for v in host[role * CAP: role * CAP + min(cnt, CAP)]:
+            lo, clk = int(v) & 0xFFFFFFFF, int(v) >> 32
+            rec.append(((role << 32) | (lo & 0xFF), lo >> 16, (lo >> 8) & 0xFF, clk))
+    # keep the tiles every role covered (the regions fill at different rates)
+    covered = min(max(r[1] for r in rec if (r[0] >> 32) == role) for role in ROLE if any((r[0] >> 32) == role for r in rec))
+    rec = [r for r in rec if r[1] <= covered]
+    n = ctypes.c_uint(len(rec))
     rec.sort(key=lambda r: r[3])
     t0 = rec[0][3]
     tiles = len({r[1] for r in rec})
