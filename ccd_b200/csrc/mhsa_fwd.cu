@@ -239,13 +239,15 @@ static int launch_mhsa_fwd(const CUtensorMap& tm, const MhsaFwdParams& p, int S,
 // ---------------------------------------------------------------------------------------------------------
 constexpr int ATT2_THREADS = 320;
 constexpr int ATT2_BUF = 3 * ATT_N * ATT_D * 2;        // Q + K + V = 96 KB
-constexpr int ATT2_SMEM = 2 * ATT2_BUF + 256 + 1024;
+constexpr int ATT2_STAGE = ATT_BM * ATT_D * 2;         // 16 KB: one [128 x 64] bf16 output tile per softmax warpgroup (TMA store)
+constexpr int ATT2_SMEM = 2 * ATT2_BUF + 2 * ATT2_STAGE + 256 + 1024;
 
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
-mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const MhsaFwdParams p, int n_items) {
+mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const MhsaFwdParams p,
+                           int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATT2_BUF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATT2_BUF + 2 * ATT2_STAGE);
   uint64_t* full_qk = bars;        // [2]
   uint64_t* full_v = bars + 2;     // [2]
   uint64_t* empty = bars + 4;      // [2]
@@ -270,6 +272,7 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmO);
   }
   pdl_launch_dependents();
   if (warp == 1) {
@@ -425,43 +428,54 @@ mhsa_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const Mhsa
       mbar_wait(&o_full[t], ph);
       tc_fence_after();
       const float inv = 1.0f / sum;
-      const size_t tok = (size_t)s * ATT_N + t * ATT_BM + r;
-      bf16* orow = p.out + tok * p.E + h * ATT_D;
-      // O leaves TMEM first and the tile is handed back (S_t of the next item may start) before the global stores
+      // O leaves TMEM first and the tile is handed back (S_t of the next item may start); the normalised bf16 rows then go to this
+      // warpgroup's 16 KB staging tile in the SWIZZLE_128B layout and leave with ONE bulk tensor store (the thread-per-row form,
+      // 8 x 16-byte global stores per thread to 32 different 128-byte lines per warp instruction, serialised in the LSU).
       uint32_t o0[32], o1[32];
       tmem_ld_32x32(tO + lane_sel, o0);
       tmem_ld_32x32(tO + lane_sel + 32, o1);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&tmem_free[t]);
+      const bool elected = (q == ((2 + 4 * t) & 3)) && lane == 0;     // lane 0 of the warpgroup's first warp
+      if (elected) tma_store_wait_read();                 // the previous item's store has finished reading the staging tile
+      named_bar_sync(1 + t, 128);
+      const uint32_t srow = smem_u32(smem + 2 * ATT2_BUF + t * ATT2_STAGE) + (uint32_t)r * 128u;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(o0[8 * g + 0]) * inv, __uint_as_float(o0[8 * g + 1]) * inv);
-        o.y = pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv);
-        o.z = pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv);
-        o.w = pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv);
-        *reinterpret_cast<uint4*>(orow + g * 8) = o;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((g ^ (r & 7)) * 16)),
+                     "r"(pack_bf16x2(__uint_as_float(o0[8 * g + 0]) * inv, __uint_as_float(o0[8 * g + 1]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv))
+                     : "memory");
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(o1[8 * g + 0]) * inv, __uint_as_float(o1[8 * g + 1]) * inv);
-        o.y = pack_bf16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv);
-        o.z = pack_bf16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv);
-        o.w = pack_bf16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv);
-        *reinterpret_cast<uint4*>(orow + 32 + g * 8) = o;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)(((4 + g) ^ (r & 7)) * 16)),
+                     "r"(pack_bf16x2(__uint_as_float(o1[8 * g + 0]) * inv, __uint_as_float(o1[8 * g + 1]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv))
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 128);
+      if (elected) {
+        tma_store_2d(&tmO, smem + 2 * ATT2_BUF + t * ATT2_STAGE, h * ATT_D, s * ATT_N + t * ATT_BM);
+        tma_store_commit();
       }
       if (p.lse2 != nullptr) p.lse2[((size_t)s * p.H + h) * ATT_N + t * ATT_BM + r] = mc + log2f(sum);
     }
   }
 
+  if (warp >= 2 && (warp & 3) == 2 && lane == 0) tma_store_wait_read();   // the elected threads: staging tiles drained before exit
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-static int launch_mhsa_fwd_persistent(const CUtensorMap& tm, const MhsaFwdParams& p, int S, cudaStream_t stream) {
+static int launch_mhsa_fwd_persistent(const CUtensorMap& tm, const CUtensorMap& tmO, const MhsaFwdParams& p, int S, cudaStream_t stream) {
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
@@ -473,7 +487,7 @@ static int launch_mhsa_fwd_persistent(const CUtensorMap& tm, const MhsaFwdParams
   }
   const int n_items = S * p.H;
   const int grid = n_items < num_sms ? n_items : num_sms;
-  CCD_CUDA_CHECK(launch_pdl(mhsa_fwd_persistent_kernel, dim3(grid), dim3(ATT2_THREADS), (size_t)ATT2_SMEM, stream, tm, p, n_items));
+  CCD_CUDA_CHECK(launch_pdl(mhsa_fwd_persistent_kernel, dim3(grid), dim3(ATT2_THREADS), (size_t)ATT2_SMEM, stream, tm, tmO, p, n_items));
   return CCD_OK;
 }
 
@@ -495,6 +509,10 @@ extern "C" int ccd_mhsa_fwd(const void* qkv, void* out, float* lse2, int S, int 
   p.H = H;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   if (variant == 1) return launch_mhsa_fwd<false>(tm, p, S, stream);
-  if (variant == 2) return launch_mhsa_fwd_persistent(tm, p, S, stream);
+  if (variant == 2) {
+    CUtensorMap tmO;                                       // output tiles leave through TMA stores
+    if (!get_tmap_bf16_2d(&tmO, out, (uint64_t)S * ATT_N, (uint64_t)E, (uint64_t)E, 128, 64)) return CCD_ERR_TMAP;
+    return launch_mhsa_fwd_persistent(tm, tmO, p, S, stream);
+  }
   return launch_mhsa_fwd<true>(tm, p, S, stream);
 }
