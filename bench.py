@@ -56,32 +56,33 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
-    `ncu --set full` summary under profiles/ (captured on this workload by tools/gpu_profile.sh); None if absent."""
+def ncu_traffic(step_shapes):
+    """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum PER LAUNCH of the dominant kernel, averaged over the GEMM
+    launches of one step exactly like `achieved` (sum over the step / launches).  Source: profiles/gemm_traffic_<round>.json, an ncu
+    pass over EVERY GEMM launch of one step with the shapes recorded in launch order (tools/gemm_traffic.py); each launch of the
+    live step is matched to its shape's measured bytes.  None when no capture is committed."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_*.json")))
-    for path in reversed(files):
-        try:
-            with open(path) as f:
-                d = json.load(f)
-        except Exception:
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "gemm_traffic_*.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    by_shape = {json.dumps(r["shape"]): r for r in d["shapes"]}
+    tot = alg = 0.0
+    matched = 0
+    for sh in step_shapes:
+        r = by_shape.get(json.dumps(list(sh) if isinstance(sh, (list, tuple)) else sh))
+        if r is None:
             continue
-        vals = []
-        for rep in d.values():
-            for k in rep:
-                if kernel_substr in k.get("kernel", ""):
-                    def mb(s):
-                        v, u = s.split()[:2]
-                        return float(v) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
-                    try:
-                        vals.append(mb(k["dram__bytes_read.sum"]) + mb(k["dram__bytes_write.sum"]))
-                    except Exception:
-                        pass
-        if vals:
-            return {"avg_mbytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals), "source": os.path.basename(path),
-                    "note": "ncu --set full, captured launches of the dominant kernel within one step (mixed shapes)"}
-    return None
+        tot += r["dram_bytes_per_launch"]; alg += r["algorithmic_bytes_per_launch"]; matched += 1
+    if not matched:
+        return None
+    top = sorted(d["shapes"], key=lambda r: -r["dram_bytes_per_launch"] * r["launches_per_step"])[:6]
+    return {"avg_mbytes_per_launch": tot / matched / 1e6, "algorithmic_avg_mbytes_per_launch": alg / matched / 1e6,
+            "launches_matched": matched, "launches_in_step": len(step_shapes), "source": os.path.basename(files[-1]),
+            "note": "ncu dram bytes of every GEMM launch of one step, matched per shape to the launches of the live step",
+            "largest_shapes": [{"shape": r["shape"], "mbytes": round(r["dram_bytes_per_launch"] / 1e6, 1),
+                                "algorithmic_mbytes": round(r["algorithmic_bytes_per_launch"] / 1e6, 1)} for r in top]}
 
 
 class ClockSampler:
@@ -284,8 +285,12 @@ def stock_cuda_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     out = {}
     for mode, ac in (("autocast_bf16", "bf16"), ("fp32", "none")):
-        env = dict(os.environ)
-        env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + (101 if ac == "bf16" else 202))   # own rendezvous per run
+        # every rank starts its own child with the launcher's RANK / LOCAL_RANK / WORLD_SIZE but WITHOUT the elastic agent's store
+        # settings (TORCHELASTIC_USE_AGENT_STORE makes rank 0 expect a TCPStore that only exists on the launcher's port: the first
+        # N = 8 attempt hung on exactly that) and on its own port, so rank 0 of the child group serves the rendezvous itself
+        env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC")}
+        env["MASTER_ADDR"] = "127.0.0.1"
+        env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + (101 if ac == "bf16" else 202))
         out[mode] = stock_cuda_run(args.arch, args.batch, args.out_dim, args.steps, max(3, args.warmup), ac, env=env)
     if rank == 0:
         print(json.dumps({"impl": "stock-cuda", "metric": METRIC, "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
@@ -481,7 +486,7 @@ def main():
     for nm in ("ccd_gemm_bf16", "ccd_conv_gemm"):
         if nm in agg:
             gemm["ms"] += agg[nm]["ms"]; gemm["flops"] += agg[nm]["flops"]; gemm["n"] += agg[nm]["n"]
-    traffic = ncu_traffic("gemm_umma_persistent_kernel")
+    traffic = ncu_traffic([w[1] for nm, w, _, _ in prof["events"] if nm in ("ccd_gemm_bf16", "ccd_conv_gemm")])
     ach = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
     roofline = {"kernel": "gemm_umma_kernel (tcgen05 GEMM, all linear contractions fwd+bwd)", "bound": "tensor",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,

@@ -80,6 +80,32 @@ if rank == 0:
         prev = nm
     gaps.sort(key=lambda g: -g[0])
     span = t1 - t0
+    # NCCL kernels run on their own stream: how much of their time is hidden under this rank's compute kernels, and how much
+    # is exposed (nothing else running on the GPU)?
+    comp = sorted((e["ts"], e["ts"] + e["dur"]) for e in ev if not e["name"].startswith("ncclDevKernel"))
+    merged = []
+    for a0, a1 in comp:
+        if merged and a0 <= merged[-1][1]:
+            merged[-1][1] = max(merged[-1][1], a1)
+        else:
+            merged.append([a0, a1])
+    import bisect
+    starts = [m[0] for m in merged]
+    nccl_total = nccl_exposed = 0.0
+    nccl_by = {}
+    for e in ev:
+        if not e["name"].startswith("ncclDevKernel"):
+            continue
+        a0, a1 = e["ts"], e["ts"] + e["dur"]
+        nccl_total += a1 - a0
+        cov = 0.0
+        i = max(0, bisect.bisect_right(starts, a0) - 1)
+        while i < len(merged) and merged[i][0] < a1:
+            cov += max(0.0, min(a1, merged[i][1]) - max(a0, merged[i][0]))
+            i += 1
+        nccl_exposed += (a1 - a0) - cov
+        k = nccl_by.setdefault(e["name"][:48], [0.0, 0.0, 0])
+        k[0] += a1 - a0; k[1] += (a1 - a0) - cov; k[2] += 1
     hist = {"<5us": 0, "5-20us": 0, "20-100us": 0, ">100us": 0}
     hsum = dict.fromkeys(hist, 0.0)
     for g in gaps:
@@ -89,11 +115,15 @@ if rank == 0:
            "gpu_busy_ms_per_step": busy / 1e3 / a.steps, "gpu_idle_ms_per_step": (span - busy) / 1e3 / a.steps,
            "n_gpu_events_per_step": len(ev) / a.steps, "gap_histogram_count": hist,
            "gap_histogram_ms_per_step": {k: v / 1e3 / a.steps for k, v in hsum.items()},
+           "nccl_ms_per_step": nccl_total / 1e3 / a.steps, "nccl_exposed_ms_per_step": nccl_exposed / 1e3 / a.steps,
+           "nccl_kernels": {k: {"ms_per_step": round(v[0] / 1e3 / a.steps, 3), "exposed_ms_per_step": round(v[1] / 1e3 / a.steps, 3),
+                                "launches_per_step": v[2] / a.steps} for k, v in nccl_by.items()},
            "largest_gaps": [{"us": round(g[0], 1), "after": g[1], "before": g[2], "at_ms": round(g[3] / 1e3, 2)} for g in gaps[:40]],
            "kernels": sorted(([k, round(v[0] / 1e3 / a.steps, 3), v[1] / a.steps] for k, v in per.items()), key=lambda r: -r[1])[:60]}
     with open(f"gpurun_out/trace_{a.tag}.json", "w") as f:
         json.dump(out, f, indent=1)
     os.remove(path)
-    print(json.dumps({k: out[k] for k in ("span_ms_per_step", "gpu_busy_ms_per_step", "gpu_idle_ms_per_step", "gap_histogram_ms_per_step")}))
+    print(json.dumps({k: out[k] for k in ("span_ms_per_step", "gpu_busy_ms_per_step", "gpu_idle_ms_per_step", "gap_histogram_ms_per_step",
+                                          "nccl_ms_per_step", "nccl_exposed_ms_per_step", "nccl_kernels")}))
 if world > 1:
     dist.destroy_process_group()
