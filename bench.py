@@ -284,7 +284,8 @@ def stock_cuda_arm(args):
     """`--impl stock-cuda`: B1 at N = WORLD_SIZE GPUs, fp32 as shipped (use_fp16: False) and under bf16 autocast."""
     rank = int(os.environ.get("RANK", "0"))
     out = {}
-    for mode, ac in (("autocast_bf16", "bf16"), ("fp32", "none")):
+    modes = [m for m in (("autocast_bf16", "bf16"), ("fp32", "none")) if m[1] in args.stock_modes.split(",")]
+    for mode, ac in modes:
         # every rank starts its own child with the launcher's RANK / LOCAL_RANK / WORLD_SIZE but WITHOUT the elastic agent's store
         # settings (TORCHELASTIC_USE_AGENT_STORE makes rank 0 expect a TCPStore that only exists on the launcher's port: the first
         # N = 8 attempt hung on exactly that) and on its own port, so rank 0 of the child group serves the rendezvous itself
@@ -358,6 +359,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stock-baseline", action="store_true", help="skip the embedded B1 sample (reference train() on this GPU)")
+    ap.add_argument("--stock-modes", default="bf16,none", help="--impl stock-cuda: which precisions to time (bf16 = autocast, none = fp32 as shipped)")
     ap.add_argument("--profile-out", default=None, help="write per-shape GEMM/attention timings (json)")
     args = ap.parse_args()
     finetune = args.workload == "finetune"
