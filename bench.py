@@ -518,7 +518,9 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "arch": args.arch, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": "inputs+activations >> L2 (20+ GB streamed per step)",
-                   "seg_head": "implicit-GEMM tcgen05 convolutions + BN kernels (ccd_conv_gemm)"},
+                   "seg_head": "implicit-GEMM tcgen05 convolutions + BN kernels (ccd_conv_gemm)",
+                   "arithmetic": "bf16 tensor-core operands, fp32 accumulate / residual stream; library built with --use_fast_math; "
+                                 "GELU epilogues = minimax fit, 2.5e-5 abs from exact erf"},
         "step_tensor_util": fs * value / world / (peak_tf * 1e12),
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "loss": final_loss,
     }
