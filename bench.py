@@ -140,37 +140,54 @@ def usable_cores():
 
 
 def cpu_reference_arm_finetune(args, as_line):
-    """Fine-tuning workload: the oracle restatement of DINO_Finetune.forward_train (oracle/finetune_oracle.py, pinned against
-    the unmodified reference) on the host cores: fwd + TFLoss + bwd of one synthetic batch, fp32, all threads."""
+    """Fine-tuning workload on the host cores: one step of train_finetune.py:283-289 (forward_train -> TFLoss -> backward -> AdamW)
+    of ViT-Small on one synthetic batch, fp32, all usable threads.  kind = "reference": the UNMODIFIED reference DINO_Finetune
+    (oracle/_ref or /root/reference); kind = "port" (oracle/finetune_oracle.py) only when the reference tree is absent."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import finetune_oracle as FO
     from ccd_b200 import synthetic as S
-    from ccd_b200.finetune import DINO_Finetune
     cores = usable_cores()
     torch.set_num_threads(cores)
     B = args.cpu_batch
-    shapes = {k: v.shape for k, v in DINO_Finetune(S.finetune_config("vit_small")).state_dict().items()}
-    sd = {k: v.requires_grad_(v.dtype.is_floating_point and "position_table" not in k) for k, v in S.fill_state_dict(shapes, 0).items()}
     img = torch.randn(B, 3, 32, 128, generator=torch.Generator().manual_seed(1234))
     tgt = S.make_targets(B, seed=1234)
     steps, warm = (args.steps, args.warmup) if as_line else (4, 1)
     budget = float(os.environ.get("CCD_CPU_BUDGET_S", "150" if as_line else "40"))
-    times, t_begin = [], time.perf_counter()
-    for i in range(warm + steps):
-        if times and time.perf_counter() - t_begin > budget:
-            break
-        t0 = time.perf_counter()
-        L, _, _ = FO.finetune_forward_train(sd, "vit_small", img, tgt)
-        L.backward()
-        for v in sd.values():
-            v.grad = None
-        if i >= warm or (i == warm - 1 and time.perf_counter() - t_begin > budget):
-            times.append(time.perf_counter() - t0)
+    import ref_import
+    if ref_import.reference_available():
+        import warnings
+        warnings.simplefilter("ignore")
+        ref = ref_import.load_reference()
+        torch.manual_seed(0)
+        model = ref.dv.DINO_Finetune(S.finetune_config("vit_small", 0.1)).train()
+        opt = torch.optim.AdamW(ref.utils.get_params_groups(model), lr=5e-4, weight_decay=0.05)
+
+        def ref_step():
+            losses, _ = model(img, tgt, return_loss=True)
+            loss = losses.mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        times = _time_cpu_steps(ref_step, steps, warm, budget)
+        kind, what = "reference", "UNMODIFIED reference DINO_Finetune (train mode, dropout 0.1) fwd+TFLoss+bwd+AdamW"
+    else:
+        import finetune_oracle as FO
+        from ccd_b200.finetune import DINO_Finetune
+        shapes = {k: v.shape for k, v in DINO_Finetune(S.finetune_config("vit_small")).state_dict().items()}
+        sd = {k: v.requires_grad_(v.dtype.is_floating_point and "position_table" not in k) for k, v in S.fill_state_dict(shapes, 0).items()}
+
+        def port_step():
+            L, _, _ = FO.finetune_forward_train(sd, "vit_small", img, tgt)
+            L.backward()
+            for v in sd.values():
+                v.grad = None
+
+        times = _time_cpu_steps(port_step, steps, warm, budget)
+        kind, what = "port", "oracle (fp32 torch restatement of the reference DINO_Finetune) fwd+TFLoss+bwd"
     sec = sum(times) / len(times)
-    cb = {"value": B / sec, "unit": "images/s", "cores": cores, "kind": "port",
-          "sample": f"oracle (fp32 torch restatement of the reference DINO_Finetune) ViT-Small fwd+TFLoss+bwd, batch {B}, "
-                    f"{len(times)} timed step(s) of {sec:.2f} s"}
+    cb = {"value": B / sec, "unit": "images/s", "cores": cores, "kind": kind,
+          "sample": f"{what}, ViT-Small, batch {B}, {len(times)} timed step(s) of {sec:.2f} s"}
     if not as_line:
         return cb
     print(json.dumps({"metric": METRIC_FT, "value": B / sec, "unit": "images/s", "n_gpus": args.gpus, "steps": len(times), "warmup": warm,

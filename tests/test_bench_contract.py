@@ -23,8 +23,8 @@ def test_reference_arm_json_line(workload, metric):
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] >= 1 and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
     import ref_import
-    # pretrain: the UNMODIFIED reference modules whenever the reference tree (or its oracle/_ref copy) is present
-    want_kind = "reference" if (workload == "pretrain" and ref_import.reference_available()) else "port"
+    # the UNMODIFIED reference modules whenever the reference tree (or its oracle/_ref copy) is present
+    want_kind = "reference" if ref_import.reference_available() else "port"
     assert cb["kind"] == want_kind and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
