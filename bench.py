@@ -213,8 +213,8 @@ def _time_cpu_steps(step_fn, steps, warm, budget):
 def cpu_reference_arm(args, as_line):
     """The reference's own CPU path on the host cores of this box: one full pretraining step (train.py:229-272: student fwd,
     teacher fwd, loss, backward, per-parameter clip, AdamW, EMA, centre) of ViT-Small on one synthetic batch, fp32, all
-    usable threads.  kind = "reference": the UNMODIFIED reference modules from /root/reference or its verbatim, hash-checked
-    copy oracle/_ref (oracle/ref_step.py); kind = "port" (the oracle restatement) only if neither is present."""
+    usable threads.  kind = "reference": the UNMODIFIED reference modules from /root/reference or the hash-checked, byte-compiled
+    tree oracle/_ref (oracle/ref_step.py); kind = "port" (the oracle restatement) only if neither is present."""
     if getattr(args, "workload", "pretrain") == "finetune":
         return cpu_reference_arm_finetune(args, as_line)
     import torch

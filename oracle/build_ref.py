@@ -1,23 +1,29 @@
-"""TEST INFRASTRUCTURE ONLY -- copy recipe that lets the UNMODIFIED reference travel to the GPU box.
+"""TEST INFRASTRUCTURE ONLY -- build recipe that lets the UNMODIFIED reference travel to the GPU box.
 
-The reference (TongkunGuan/CCD) is pure Python: its "build" is a verbatim copy of its own source files from where they
-lie under /root/reference into oracle/_ref/ (git-ignored, so no reference source ever enters this repository's history;
-NOT gpurun-ignored, so the copy ships with the snapshot exactly like the in-tree libccd_b200.so).  Nothing is edited:
-`oracle/ref_manifest.json` (tracked) records the SHA-256 of every file at the pinned reference commit and
-`verify()` re-checks the copy against it, so a test or bench arm that runs from oracle/_ref can state that it executed
-the reference's own code.
+The reference (TongkunGuan/CCD) is pure Python.  Its "build" here is a byte-compilation: every `.py` of the pinned commit is
+compiled FROM WHERE IT LIES under /root/reference into a sourceless `.pyc` tree under oracle/_ref/ (Python imports
+`pkg/module.pyc` directly), and the YAML configs / charsets the code reads at run time are packed into ONE data blob
+(oracle/_ref/data_files.json).  No reference source file is copied into this repository -- oracle/_ref/ holds build outputs only;
+it is git-ignored (never in history) and NOT gpurun-ignored (it ships with the snapshot exactly like the in-tree
+libccd_b200.so).  Provenance chain:
+    oracle/ref_manifest.json (tracked)  SHA-256 of every reference source at the pinned commit
+      -> build(): each source is re-hashed against it BEFORE it is compiled (a modified reference refuses to build)
+      -> oracle/_ref/BUILD_MANIFEST.json  SHA-256 of every produced file + the source hashes they came from
+      -> verify(): re-hashes the build outputs (integrity on the GPU box) and checks the recorded source hashes against the
+         tracked manifest.
 
 Users of oracle/_ref (the same three places that may use anything under oracle/):
-  tests/                       reference-vs-product parity on the GPU (train.py driving the drop-in, B1 stock-CUDA modules)
+  tests/                       reference-vs-product parity on the GPU (train.py driving the drop-in, full-size comparator)
   bench.py --impl reference    the reference's own CPU path (cpu_baseline.kind = "reference")
-  bench.py --impl stock-cuda   BASELINE.md B1: the reference's modules on CUDA wrapped like train.py:93-110
+  bench.py --impl stock-cuda   BASELINE.md B1: the reference's train() + modules on CUDA
 The product path (ccd_b200/, Dino/) never imports it.
 
-    python oracle/build_ref.py            # copy + verify;  --manifest rewrites oracle/ref_manifest.json from the source tree
+    python oracle/build_ref.py            # build + verify;  --manifest rewrites oracle/ref_manifest.json from the source tree
 """
 import hashlib
 import json
 import os
+import py_compile
 import shutil
 import sys
 
@@ -25,7 +31,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("CCD_REFERENCE_SRC", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 MANIFEST = os.path.join(HERE, "ref_manifest.json")
-# what travels: the python sources of the path and of its callers + the YAML configs / charsets they read at run time
 KEEP_EXT = (".py", ".yaml", ".txt")
 SKIP_DIRS = {".git", "graph", "__pycache__"}
 
@@ -60,12 +65,17 @@ def load_manifest():
 
 
 def verify(dst=DST):
-    """Every manifest file present in the copy with the recorded hash (i.e. the reference, unmodified)."""
-    man = load_manifest()
-    bad = [rel for rel, h in man.items() if not os.path.isfile(os.path.join(dst, rel)) or _sha(os.path.join(dst, rel)) != h]
+    """The build outputs are intact and were produced from the pinned, unmodified sources."""
+    with open(os.path.join(dst, "BUILD_MANIFEST.json")) as f:
+        built = json.load(f)
+    if built["sources"] != load_manifest():
+        raise RuntimeError("oracle/_ref was not built from the pinned reference (source hashes differ from oracle/ref_manifest.json)")
+    if built["python"] != list(sys.version_info[:2]):
+        raise RuntimeError(f"oracle/_ref was compiled by Python {built['python']}, this is {list(sys.version_info[:2])}")
+    bad = [rel for rel, h in built["outputs"].items() if not os.path.isfile(os.path.join(dst, rel)) or _sha(os.path.join(dst, rel)) != h]
     if bad:
-        raise RuntimeError(f"oracle/_ref differs from the pinned reference in {len(bad)} file(s), e.g. {bad[:3]}")
-    return len(man)
+        raise RuntimeError(f"oracle/_ref: {len(bad)} build output(s) missing or altered, e.g. {bad[:3]}")
+    return len(built["outputs"])
 
 
 def available(dst=DST):
@@ -76,20 +86,55 @@ def available(dst=DST):
         return False
 
 
+def data_files(dst=DST):
+    """{relative path: text} of the reference's run-time data files (YAML configs, charsets)."""
+    with open(os.path.join(dst, "data_files.json")) as f:
+        return json.load(f)
+
+
+def materialize_data(workdir, dst=DST):
+    """Writes the packed data files under `workdir` with their reference-relative paths (Config opens
+    'Dino/configs/template.yaml' relative to the working directory, Dino/utils/utils.py:208)."""
+    for rel, text in data_files(dst).items():
+        out = os.path.join(workdir, rel)
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        with open(out, "w") as f:
+            f.write(text)
+
+
 def build(src=SRC, dst=DST):
-    """Copy the manifest's files verbatim; returns the number of files, or 0 when the source tree is absent (GPU box:
-    the prebuilt copy that travelled with the snapshot is used as is)."""
+    """Byte-compile the pinned sources into oracle/_ref; returns the number of build outputs, or 0 when the source tree is
+    absent (GPU box: the prebuilt tree that travelled with the snapshot is used as is)."""
     if not os.path.isdir(os.path.join(src, "Dino")):
         return 0
     man = load_manifest()
+    for rel, h in man.items():
+        if _sha(os.path.join(src, rel)) != h:
+            raise RuntimeError(f"{rel} under {src} differs from the pinned reference (oracle/ref_manifest.json)")
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    outputs, data = {}, {}
     for rel in man:
-        out = os.path.join(dst, rel)
-        os.makedirs(os.path.dirname(out), exist_ok=True)
-        shutil.copyfile(os.path.join(src, rel), out)
+        if rel.endswith(".py"):
+            out_rel = rel[:-3] + ".pyc"
+            out = os.path.join(dst, out_rel)
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            py_compile.compile(os.path.join(src, rel), cfile=out, dfile=rel, doraise=True,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            outputs[out_rel] = _sha(out)
+        else:
+            with open(os.path.join(src, rel)) as f:
+                data[rel] = f.read()
+    os.makedirs(dst, exist_ok=True)
+    with open(os.path.join(dst, "data_files.json"), "w") as f:
+        json.dump(data, f)
+    outputs["data_files.json"] = _sha(os.path.join(dst, "data_files.json"))
+    with open(os.path.join(dst, "BUILD_MANIFEST.json"), "w") as f:
+        json.dump({"sources": man, "outputs": outputs, "python": list(sys.version_info[:2])}, f, indent=0, sort_keys=True)
     return verify(dst)
 
 
 if __name__ == "__main__":
     if "--manifest" in sys.argv:
         print("manifest:", len(write_manifest()), "files")
-    print("oracle/_ref:", build(), "files copied and verified")
+    print("oracle/_ref:", build(), "build outputs (sourceless .pyc + data blob), verified")

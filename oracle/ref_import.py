@@ -2,8 +2,8 @@
 in this container so the oracle restatement (oracle/ccd_oracle.py) can be pinned against it and golden
 vectors can be generated (tests/golden/make_golden.py).
 
-/root/reference does not exist on the GPU box; there the reference is the verbatim, hash-verified copy
-oracle/_ref made by oracle/build_ref.py (git-ignored, travels with the snapshot).  Users: tests/, bench.py's reference
+/root/reference does not exist on the GPU box; there the reference is the hash-verified, byte-compiled tree
+oracle/_ref built by oracle/build_ref.py (build outputs only, git-ignored, travels with the snapshot).  Users: tests/, bench.py's reference
 arms (--impl reference / stock-cuda) and nothing else; the product path never imports this module.  Only third-party *imports* that are missing from this image are stubbed; no reference
 arithmetic is replaced except skimage.measure.label, which is restated with scipy.ndimage.label
 (8-connectivity, raster-order labels -- the same labelling skimage's default connectivity produces;
@@ -23,9 +23,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _find_reference():
-    """CCD_REFERENCE_ROOT if set; else the reference checkout of this container; else the verbatim copy that
-    oracle/build_ref.py made of it (oracle/_ref, hash-checked against oracle/ref_manifest.json) -- the only form in which the
-    reference reaches the GPU box."""
+    """CCD_REFERENCE_ROOT if set; else the reference checkout of this container; else the sourceless byte-compiled tree that
+    oracle/build_ref.py built from it (oracle/_ref, hash-checked against oracle/ref_manifest.json) -- the only form in which
+    the reference reaches the GPU box."""
     env = os.environ.get("CCD_REFERENCE_ROOT")
     if env:
         return env
@@ -39,6 +39,11 @@ REFERENCE_ROOT = _find_reference()
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "Dino"))
+
+
+def reference_sources_available() -> bool:
+    """True only for a SOURCE checkout (tests that read the reference's text, e.g. an ast scan of train.py)."""
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "train.py"))
 
 
 def _mod(name, **attrs):

@@ -1,5 +1,5 @@
 """TEST / BASELINE INFRASTRUCTURE -- one CCD pretraining step computed by the UNMODIFIED reference modules
-(/root/reference, or its verbatim hash-checked copy oracle/_ref on the GPU box), on any device.
+(/root/reference, or the hash-checked byte-compiled tree oracle/_ref on the GPU box), on any device.
 
 The loop body below is this harness's own (the reference's `train()` needs CUDA, NCCL and LMDB data; oracle/run_ref_train.py
 runs that one on a GPU); every quantity is produced by the reference's classes:

@@ -1,5 +1,5 @@
 """TEST / BASELINE INFRASTRUCTURE -- runs the reference's OWN `train()` (train.py:45-302, unmodified, from /root/reference or
-its verbatim copy oracle/_ref) for a few iterations on synthetic batches, with either
+its byte-compiled copy oracle/_ref, see oracle/build_ref.py) for a few iterations on synthetic batches, with either
 
   --impl reference   the reference's own modules (stock PyTorch-CUDA path = BASELINE.md B1: SyncBN convert, teacher DDP,
                      student DDP(find_unused_parameters=True), per-parameter clip with .item(), torch.optim.AdamW, the
@@ -94,9 +94,15 @@ def main():
     import yaml
 
     work = tempfile.mkdtemp(prefix=f"ccd_ref_train_{args.impl}_r{rank}_")
-    os.symlink(os.path.join(ref_root, "Dino"), os.path.join(work, "Dino"))        # Config reads Dino/configs/template.yaml from CWD
+    # Config reads Dino/configs/template.yaml relative to the working directory (Dino/utils/utils.py:208)
+    if os.path.isfile(os.path.join(ref_root, "data_files.json")):               # the compiled copy oracle/_ref: unpack its data blob
+        build_ref = _load_by_path("build_ref", os.path.join(HERE, "build_ref.py"))
+        build_ref.verify(ref_root)
+        build_ref.materialize_data(work, ref_root)
+    else:                                                                        # a source checkout
+        os.symlink(os.path.join(ref_root, "Dino"), os.path.join(work, "Dino"))
     os.chdir(work)
-    with open(os.path.join(ref_root, "Dino", "configs", "CCD_pretrain_ViT_small.yaml")) as f:
+    with open(os.path.join(work, "Dino", "configs", "CCD_pretrain_ViT_small.yaml")) as f:
         cfg = yaml.load(f, Loader=yaml.FullLoader)
     E = {"vit_tiny": 192, "vit_small": 384, "vit_base": 512}[args.arch]
     cfg.update(arch=args.arch, out_dim=args.out_dim, batch_size_per_gpu=args.batch, drop_path_rate=args.drop_path, warmup_epoch=0,

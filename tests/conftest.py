@@ -18,7 +18,7 @@ def pytest_collection_modifyitems(config, items):
     import torch
     has_gpu = torch.cuda.is_available()
     import ref_import
-    has_ref = ref_import.reference_available()          # /root/reference here, its verbatim copy oracle/_ref on the GPU box
+    has_ref = ref_import.reference_available()          # /root/reference here, the byte-compiled tree oracle/_ref on the GPU box
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))

@@ -1,6 +1,6 @@
 """BASELINE config 2 EXACTLY (ViT-Small, batch 256, 2 views, out_dim 65536) on the GPU: the sm_100a path against the UNMODIFIED
-reference modules run in fp32 eager PyTorch on the same device, same weights, same inputs (oracle/ref_step.py from the verbatim
-copy oracle/_ref).  This is the configuration bench.py's number is quoted on.  Bars: loss rel-err <= 1e-3, logits atol <= 1e-2,
+reference modules run in fp32 eager PyTorch on the same device, same weights, same inputs (oracle/ref_step.py from the byte-compiled
+tree oracle/_ref).  This is the configuration bench.py's number is quoted on.  Bars: loss rel-err <= 1e-3, logits atol <= 1e-2,
 cluster maps / index / warped GT bit-exact, centre after one update, and the full-size gradients by cosine."""
 import os
 import sys
@@ -20,7 +20,7 @@ def _reference_or_skip():
         pytest.skip("no reference tree (oracle/_ref is built by __graft_entry__.build() where /root/reference exists)")
     if "_ref" in ref_import.REFERENCE_ROOT:
         import build_ref
-        build_ref.verify()                       # the copy is the pinned reference, byte for byte
+        build_ref.verify()                       # built from the pinned, unmodified sources; outputs intact
     return ref_import
 
 
