@@ -486,7 +486,7 @@ def main():
                          f"{args.arch} batch {B}, out_dim {args.out_dim}, synthetic batches, 1 GPU", "unit": "images/s"}
         for mode, ac, port in (("autocast_bf16", "bf16", 29711), ("fp32", "none", 29712)):
             env["MASTER_PORT"] = str(port)
-            stock[mode] = stock_cuda_run(args.arch, B, args.out_dim, int(os.environ.get("CCD_STOCK_STEPS", "8")), 3, ac, timeout_s=600, env=env)
+            stock[mode] = stock_cuda_run(args.arch, B, args.out_dim, int(os.environ.get("CCD_STOCK_STEPS", "8")), 3, ac, timeout_s=300, env=env)
     if rank != 0:
         if ddp:
             dist.destroy_process_group()
