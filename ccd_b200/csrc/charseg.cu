@@ -477,6 +477,41 @@ __global__ void __launch_bounds__(256) kmeans_mask_kernel(const uint8_t* __restr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Affine theta of the irregular view (datasetsupervised_kmeans.py:60-71; SURVEY section 8f #4, second slice -- the algebra only).
+// The dataset draws an imgaug Affine, takes the INVERSE pixel-space matrix M_inv of the warp it applied to the source-size
+// image (`matric[0]._inv_matrix`), rescales it to the 128 x 32 network input and re-expresses it in grid_sample's normalised
+// coordinates:   metric = W^-1 M_inv W,   theta = N metric N^-1,   W = diag(src_w / img_w, src_h / img_h, 1),
+//                N = [[2/(img_w-1), 0, -1], [0, 2/(img_h-1), -1], [0, 0, 1]]          (float64, stored as float32).
+// One thread per sample.  Drawing the augmentation parameters and building M_inv stay with imgaug (third party, not in this
+// image): this kernel replaces lines 63-71 for a batch of matrices.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat3_mul(const double (&a)[9], const double (&b)[9], double (&c)[9]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+__global__ void affine_theta_kernel(const double* __restrict__ m_inv, const int* __restrict__ src_hw, float* __restrict__ theta, int n,
+                                    int img_h, int img_w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ws = (double)src_hw[2 * i + 1] / (double)img_w, hs = (double)src_hw[2 * i] / (double)img_h;
+  const double Wi[9] = {1.0 / ws, 0, 0, 0, 1.0 / hs, 0, 0, 0, 1}, W[9] = {ws, 0, 0, 0, hs, 0, 0, 0, 1};
+  const double N[9] = {2.0 / (img_w - 1), 0, -1, 0, 2.0 / (img_h - 1), -1, 0, 0, 1};
+  const double Ni[9] = {(img_w - 1) / 2.0, 0, (img_w - 1) / 2.0, 0, (img_h - 1) / 2.0, (img_h - 1) / 2.0, 0, 0, 1};
+  double M[9], t0[9], metric[9], t1[9], th[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M[k] = m_inv[9 * i + k];
+  mat3_mul(Wi, M, t0);
+  mat3_mul(t0, W, metric);
+  mat3_mul(N, metric, t1);
+  mat3_mul(t1, Ni, th);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) theta[9 * i + k] = (float)th[k];
+}
+
 }  // namespace ccd
 
 using namespace ccd;
@@ -490,6 +525,13 @@ extern "C" int ccd_ccl_label(const float* src, int mode, void* bits_u32, void* c
     attr_set = true;
   }
   ccl_label_kernel<<<n_img, 256, smem, (cudaStream_t)stream>>>(src, mode, (unsigned*)bits_u32, (unsigned char*)compact_u8, n_comp);
+  CCD_LAUNCH_CHECK();
+  return CCD_OK;
+}
+
+extern "C" int ccd_affine_theta(const double* m_inv, const int* src_hw, float* theta, int n, int img_h, int img_w, void* stream) {
+  if (!m_inv || !src_hw || !theta || n <= 0 || img_h < 2 || img_w < 2) return CCD_ERR_ARG;
+  affine_theta_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(m_inv, src_hw, theta, n, img_h, img_w);
   CCD_LAUNCH_CHECK();
   return CCD_OK;
 }

@@ -431,6 +431,15 @@ def kmeans_mask(grey_u8):
     return out
 
 
+def affine_theta(m_inv, src_hw, img_h=32, img_w=128):
+    """Thetas of the irregular view from imgaug's inverse pixel-space matrices (datasetsupervised_kmeans.py:63-71):
+    m_inv f64 [n,3,3], src_hw int32 [n,2] (h, w) -> f32 [n,3,3]."""
+    n = m_inv.shape[0]
+    out = torch.empty(n, 3, 3, dtype=torch.float32, device=m_inv.device)
+    _call("ccd_affine_theta", _p(_chk(m_inv, torch.float64)), _p(_chk(src_hw, torch.int32)), _p(out), n, img_h, img_w, _s())
+    return out
+
+
 def warp_bits(bits, theta):
     out = torch.empty_like(bits)
     _call("ccd_warp_bits", _p(bits), _p(_chk(theta, torch.float32)), _p(out), bits.shape[0], _s())

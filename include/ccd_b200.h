@@ -126,6 +126,9 @@ int ccd_ccl_label(const float* src, int mode, void* bits_u32, void* compact_u8, 
  * (histogram + threshold scan) + the border-majority polarity flip.  grey u8 [n,H,W] -> mask f32 {0,1} [n,H,W] (text = 1), the
  * form ccd_ccl_label mode 0 consumes.  H*W <= 2^20. */
 int ccd_kmeans_mask(const void* grey_u8, float* mask, int n_img, int H, int W, void* stream);
+/* Affine theta of the irregular view from the inverse pixel-space warp matrices (datasetsupervised_kmeans.py:63-71):
+ * m_inv f64 [n,3,3], src_hw int32 [n,2] (height, width of each source image) -> theta f32 [n,3,3] for F.affine_grid at img_h x img_w. */
+int ccd_affine_theta(const double* m_inv, const int* src_hw, float* theta, int n, int img_h, int img_w, void* stream);
 /* affine_grid + bilinear grid_sample(zeros, align_corners=False) + (> 0.1): dino_vision.py:72-77, train.py:234-236 */
 int ccd_warp_bits(const void* src_bits, const float* theta, void* dst_bits, int n_img, void* stream);
 int ccd_warp_mask(const float* src, const float* theta, float* dst, int n_img, void* stream);

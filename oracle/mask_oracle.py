@@ -87,3 +87,16 @@ def synthetic_text_crops(n, h=32, w=128, seed=0, noise=12.0):
         img += g.normal(0, noise, size=(h, w))
         out[i] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
     return out
+
+
+def affine_theta(m_inv, src_h, src_w, img_h=32, img_w=128):
+    """datasetsupervised_kmeans.py:63-71, line for line (numpy float64, cast to float32 as :87 does): `m_inv` is imgaug's
+    `matric[0]._inv_matrix` of the warp applied to the source-size image."""
+    W_scale = src_w / img_w
+    H_scale = src_h / img_h
+    W_inv = np.array([[1 / W_scale, 0, 0], [0, 1 / H_scale, 0], [0, 0, 1]])
+    W = np.array([[W_scale, 0, 0], [0, H_scale, 0], [0, 0, 1]])
+    metric = np.matmul(np.matmul(W_inv, m_inv), W)
+    W_ = np.array([[2 / (img_w - 1), 0, -1], [0, 2 / (img_h - 1), -1], [0, 0, 1]])
+    theta = np.matmul(np.matmul(W_, metric), np.linalg.inv(W_))
+    return np.array(theta, dtype=np.float32)

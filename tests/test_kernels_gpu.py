@@ -566,3 +566,32 @@ def test_kmeans_mask_bit_exact_vs_oracle_and_reference_golden(ops):
     for i in range(8):
         _, want = O.label_cluster(MO.cluster_pixels(imgs[i]).astype(np.float32))
         assert np.array_equal(compact[i].cpu().numpy(), want), i
+
+
+def test_affine_theta_matches_the_dataset_algebra(ops):
+    """ccd_affine_theta against the line-for-line numpy restatement of datasetsupervised_kmeans.py:63-71, and the end-to-end meaning
+    of the result: warping with theta through F.affine_grid / grid_sample reproduces the pixel-space warp the matrix describes."""
+    import mask_oracle as MO
+    g = np.random.default_rng(5)
+    n = 64
+    m_inv = np.tile(np.eye(3), (n, 1, 1))
+    hw = np.stack([g.integers(24, 200, n), g.integers(60, 600, n)], 1).astype(np.int32)
+    for i in range(1, n):                                    # sample 0 stays the identity
+        a, sh = g.uniform(-0.17, 0.17), g.uniform(-0.6, 0.6)
+        sx, sy = g.uniform(0.6, 1.1), g.uniform(0.6, 1.1)
+        fwd = np.array([[sx * np.cos(a), -sy * np.sin(a + sh), g.uniform(-5, 5)], [sx * np.sin(a), sy * np.cos(a + sh), g.uniform(-2, 2)], [0, 0, 1]])
+        m_inv[i] = np.linalg.inv(fwd)
+    got = ops.affine_theta(torch.from_numpy(m_inv).cuda(), torch.from_numpy(hw).cuda()).cpu().numpy()
+    for i in range(n):
+        want = MO.affine_theta(m_inv[i], int(hw[i, 0]), int(hw[i, 1]))
+        assert np.allclose(got[i], want, rtol=2e-6, atol=2e-6), (i, got[i], want)
+    assert np.allclose(got[0], np.eye(3), atol=1e-7)
+    # meaning: theta maps normalised output coordinates to normalised input coordinates of the 32 x 128 crop
+    i = 7
+    th = torch.from_numpy(got[i:i + 1, :2, :])
+    grid = torch.nn.functional.affine_grid(th, (1, 1, 32, 128), align_corners=True)       # N = [[2/(w-1),0,-1],...] is the align_corners=True map
+    ys, xs = 11, 57
+    ws, hs = hw[i, 1] / 128.0, hw[i, 0] / 32.0
+    src_px = m_inv[i] @ np.array([xs * ws, ys * hs, 1.0])
+    want_norm = np.array([src_px[0] / ws * 2 / 127 - 1, src_px[1] / hs * 2 / 31 - 1])
+    assert np.allclose(grid[0, ys, xs].numpy(), want_norm, atol=1e-4)
