@@ -77,3 +77,33 @@ def test_oracle_matches_reference_live():
         agree.append(_compare(im, ref, MO.cluster_pixels(im)))
     agree = [a for a in agree if a is not None]
     assert min(agree) >= 0.985 and sum(a == 1.0 for a in agree) >= 0.85 * len(agree)
+
+
+def test_threshold_scan_minimises_the_two_means_distortion():
+    """The histogram scan maximises s0^2/n0 + s1^2/n1, i.e. minimises the k-means distortion sum |v - c(v)|^2 over all threshold
+    partitions -- checked by brute force -- and the partition is a Lloyd fixed point (nearest-centroid assignment reproduces it)."""
+    g = np.random.default_rng(0)
+    for trial in range(40):
+        n = int(g.integers(20, 400))
+        vals = np.clip(np.rint(np.concatenate([g.normal(g.uniform(20, 120), g.uniform(3, 25), n),
+                                               g.normal(g.uniform(130, 240), g.uniform(3, 25), int(g.integers(5, 300)))])), 0, 255).astype(np.uint8)
+        im = vals.reshape(1, -1)
+        t, c0, c1 = MO.two_means_threshold(im)
+        v = vals.astype(np.float64)
+
+        def sse(th):
+            a, b = v[v <= th], v[v > th]
+            return ((a - a.mean()) ** 2).sum() + ((b - b.mean()) ** 2).sum() if len(a) and len(b) else np.inf
+        best = min(sse(th) for th in range(255))
+        assert abs(sse(t) - best) <= 1e-9 * max(1.0, best)
+        mid = 0.5 * (c0 + c1)
+        assert np.array_equal(v > mid, v > t)            # a fixed point of Lloyd's iteration
+
+
+def test_affine_theta_identity_and_scaling():
+    th = MO.affine_theta(np.eye(3), 64, 300)
+    assert np.allclose(th, np.eye(3), atol=1e-7)
+    # a pure translation by (dx, dy) source pixels becomes 2 dx / ((w_src / 128) * 127) in normalised units
+    m = np.eye(3); m[0, 2], m[1, 2] = 30.0, -4.0
+    th = MO.affine_theta(m, 64, 256)
+    assert np.allclose(th[0, 2], 30.0 / 2.0 * 2 / 127, atol=1e-6) and np.allclose(th[1, 2], -4.0 / 2.0 * 2 / 31, atol=1e-6)
