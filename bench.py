@@ -444,12 +444,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    t_host0 = time.perf_counter()
+    host_enqueue_ms = None
     for k in range(K):
         if k == K - 1:
             ops.PROFILE = prof
+        t_host0 = time.perf_counter()
         loss = trainer.step(*resident, sync_loss=False)
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K      # how long the host needs to ENQUEUE a step (no waiting inside)
+        if k == 0:      # the launch queue is empty right after the barrier: this is pure enqueue time, no back-pressure from the GPU
+            host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     e1.record()
     barrier()
     ops.PROFILE = None
@@ -542,7 +544,7 @@ def main():
                                  "GELU epilogues = minimax fit, 2.5e-5 abs from exact erf"},
         "step_tensor_util": fs * value / world / (peak_tf * 1e12),
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "loss": final_loss,
-        # diagnostic: host time to enqueue one step of timed region 1 (includes the per-launch event records of the last step); when it
+        # diagnostic: host time to enqueue the first timed step (empty launch queue, so no back-pressure from the GPU); when it
         # approaches ms_per_step the step is host-bound on this box, which is what separates `e2e` from `value` on slow hosts
         "host_enqueue_ms_per_step": host_enqueue_ms,
     }
