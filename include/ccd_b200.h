@@ -60,7 +60,8 @@ int ccd_mhsa_bwd(const void* qkv, const void* o, const void* d_o, const float* l
 /* C[M,N] = op(A) B in f32 for the small constant operators of the path: the 256 x 256 bicubic resample of pos_embed
  * (interpolate_pos_encoding, vision_transformer.py:182-201) and its transpose in the backward.  trans_a: A stored [K,M]. */
 int ccd_smallmm_f32(const float* A, const float* B, float* C, int M, int N, int K, int trans_a, void* stream);
-/* out[c] += sum_r v[r] * W[r, c]   (f32, W row-major [rows, cols]) */
+/* out[c] += sum_r v[r] * W[r, c]   (f32, W row-major [rows, cols]).  On the path: the v part of the Attention.qkv.bias gradient
+ * (vision_transformer.py:82) = (Attention.proj.bias gradient) . W_proj, see ccd_mhsa_bwd. */
 int ccd_vecmat_add_f32(const float* v, const float* W, float* out, int rows, int cols, void* stream);
 /* A/B switch (debug): 1 = pipelined persistent backward kernel (default), 0 = first version (one CTA per (sequence, head)) */
 int ccd_set_mhsa_bwd_variant(int value);
