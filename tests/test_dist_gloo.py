@@ -71,3 +71,42 @@ def test_reference_update_center_single_rank_matches_oracle():
     want = O.updated_center(crit.center.clone(), zt)
     crit.update_center(zt)
     assert (crit.center - want).abs().max() < 1e-7
+
+
+def _host_worker(rank, world, port, tmp, q):
+    """The host-side helpers train.py calls under N > 1 (Dino.modules.utils -> ccd_b200/host_utils.py) in a 2-rank gloo group."""
+    import contextlib
+    import io
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root]
+    from Dino.modules import utils
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    assert utils.get_world_size() == world and utils.get_rank() == rank and utils.is_main_process() == (rank == 0)
+    path = os.path.join(tmp, f"ckpt_{rank}.pth")
+    utils.save_on_master({"epoch": 5, "iteration": 9}, path)          # only rank 0 writes (train.py:204-207)
+    utils.setup_for_distributed(rank == 0)                            # print() is silent on the other ranks unless force=True
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        print("log line")
+        print("fatal", force=True)
+    dist.barrier()
+    q.put((rank, os.path.exists(path), buf.getvalue()))
+    dist.destroy_process_group()
+
+
+def test_host_helpers_two_ranks(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_host_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = {r: (wrote, out) for r, wrote, out in (q.get(timeout=10), q.get(timeout=10))}
+    assert got[0] == (True, "log line\nfatal\n")
+    assert got[1] == (False, "fatal\n")
